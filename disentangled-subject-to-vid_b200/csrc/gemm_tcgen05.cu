@@ -1,0 +1,337 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  Y[M,N] = X[M,K] W[N,K]^T (+ T[M,r] B[N,r]^T) with fused epilogues.
+//
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 2D, 128B swizzle, BLOCK_K = 64 bf16 = one swizzle row)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M = 128, N = BN, K = 16 per instruction)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> bias / GELU / gate-residual -> 16-byte global stores)
+//
+// Accumulators are double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile
+// i+1.  Tiles are rasterised in groups of GROUP_M row-blocks so that one wave of 148 CTAs re-uses both the activation
+// panel and the weight panel out of the 126 MB L2.  The LoRA up-projection is folded in as extra K blocks read through
+// a second pair of tensor maps (no concatenated copies are materialised).
+#include "common.cuh"
+#include "host_util.h"
+#include "s2v_b200.h"
+
+namespace s2v {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_GROUP_M = 16;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmKParams {
+    int M, N, K, K2;
+    int lora_group_n;
+    const bf16* bias;
+    bf16* out;
+    long long ldo;
+    float alpha;
+    const float* mod;
+    int mod_stride, gate_off_text, gate_off_other, rows_per_batch, text_len;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+    const int per_group = GEMM_GROUP_M * num_n;
+    const int g = tile / per_group;
+    const int r = tile - g * per_group;
+    const int m_first = g * GEMM_GROUP_M;
+    const int gm = min(GEMM_GROUP_M, num_m - m_first);
+    m_blk = m_first + r % gm;
+    n_blk = r / gm;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                    const GemmKParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + Cfg::STAGES;
+    uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int num_n = (p.N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int kb1 = (p.K + GEMM_BK - 1) / GEMM_BK;
+    const int kb2 = (p.K2 + GEMM_BK - 1) / GEMM_BK;
+    const int kb_total = kb1 + kb2;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (kb2) {
+            tma_prefetch_desc(&tmA2);
+            tma_prefetch_desc(&tmB2);
+        }
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(tile, num_m, num_n, m_blk, n_blk);
+                const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+                const int lora_col0 = kb2 ? (n0 / p.lora_group_n) * p.K2 : 0;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if (kb < kb1) {
+                        tma_load_2d(&tmA, &full_bar[stage], sa, kb * GEMM_BK, m0);
+                        tma_load_2d(&tmB, &full_bar[stage], sb, kb * GEMM_BK, n0);
+                    } else {
+                        const int kk = (kb - kb1) * GEMM_BK;
+                        tma_load_2d(&tmA2, &full_bar[stage], sa, lora_col0 + kk, m0);
+                        tma_load_2d(&tmB2, &full_bar[stage], sb, kk, n0);
+                    }
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < kb_total; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) field
+                        umma_ss(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;  // TMEM lane quarter this warp may touch
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            int m_blk, n_blk;
+            tile_coords(tile, num_m, num_n, m_blk, n_blk);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * GEMM_BM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const int n0 = n_blk * BN;
+            bf16* orow = p.out + (long long)row * p.ldo + n0;
+            const float* gate = nullptr;
+            if (EPI == S2V_EPI_GATE_RESIDUAL && row_ok) {
+                const int b = row / p.rows_per_batch;
+                const int s = row - b * p.rows_per_batch;
+                gate = p.mod + (long long)b * p.mod_stride + (s < p.text_len ? p.gate_off_text : p.gate_off_other) + n0;
+            }
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * 32, v);
+                tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                if (row_ok && col0 < p.N) {
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const int col = col0 + g8 * 8;
+                        if (col < p.N) {
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g8 * 8 + j]) * p.alpha;
+                            if (p.bias) {
+                                const uint4 bb = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+                                const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    f[2 * j] += bf16_lo(bw[j]);
+                                    f[2 * j + 1] += bf16_hi(bw[j]);
+                                }
+                            }
+                            if (EPI == S2V_EPI_BIAS_GELU) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
+                            }
+                            if (EPI == S2V_EPI_GATE_RESIDUAL) {
+                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + c * 32 + g8 * 8));
+                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + c * 32 + g8 * 8 + 4));
+                                const uint4 rr = *reinterpret_cast<const uint4*>(orow + c * 32 + g8 * 8);
+                                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+                                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    f[2 * j] = bf16_lo(rw[j]) + gg[2 * j] * f[2 * j];
+                                    f[2 * j + 1] = bf16_hi(rw[j]) + gg[2 * j + 1] * f[2 * j + 1];
+                                }
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(f[0], f[1]);
+                            o.y = pack_bf16x2(f[2], f[3]);
+                            o.z = pack_bf16x2(f[4], f[5]);
+                            o.w = pack_bf16x2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(orow + c * 32 + g8 * 8) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------ host side
+template <int BN, int EPI>
+static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap tmA, tmB, tmA2, tmB2;
+    int rc;
+    if ((rc = make_tmap_2d_bf16(&tmA, a->x, a->K, a->M, a->ldx, GEMM_BK, GEMM_BM))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tmB, a->w, a->K, a->N, a->ldw, GEMM_BK, BN))) return rc;
+    const int K2 = a->lora_t ? a->lora_r : 0;
+    if (K2) {
+        const int groups = (a->N + a->lora_group_n - 1) / a->lora_group_n;
+        if ((rc = make_tmap_2d_bf16(&tmA2, a->lora_t, (int64_t)groups * K2, a->M, a->ldt, GEMM_BK, GEMM_BM))) return rc;
+        if ((rc = make_tmap_2d_bf16(&tmB2, a->lora_b, K2, a->N, a->ldb, GEMM_BK, BN))) return rc;
+    } else {
+        tmA2 = tmA;
+        tmB2 = tmB;
+    }
+    GemmKParams p;
+    p.M = a->M; p.N = a->N; p.K = a->K; p.K2 = K2;
+    p.lora_group_n = a->lora_group_n > 0 ? a->lora_group_n : a->N;
+    p.bias = static_cast<const bf16*>(a->bias);
+    p.out = static_cast<bf16*>(a->out);
+    p.ldo = a->ldo;
+    p.alpha = a->alpha;
+    p.mod = a->mod;
+    p.mod_stride = a->mod_stride; p.gate_off_text = a->gate_off_text; p.gate_off_other = a->gate_off_other;
+    p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->M; p.text_len = a->text_len;
+
+    auto kern = gemm_tcgen05_kernel<BN, EPI>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
+        attr_done = true;
+    }
+    const int num_tiles = ((a->M + GEMM_BM - 1) / GEMM_BM) * ((a->N + BN - 1) / BN);
+    const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+    return check_launch("gemm_tcgen05_kernel");
+}
+
+}  // namespace s2v
+
+using namespace s2v;
+
+extern "C" int s2v_linear(const s2v_linear_args* a, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!a || !a->x || !a->w || !a->out) return set_error(S2V_E_BADARG, "s2v_linear: null pointer");
+    if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(S2V_E_BADARG, "s2v_linear: empty problem");
+    if ((a->K % 8) || (a->N % 8) || (a->ldx % 8) || (a->ldw % 8) || (a->ldo % 8))
+        return set_error(S2V_E_UNSUPPORTED, "s2v_linear: K, N and leading dims must be multiples of 8 (16-byte rows)");
+    if (a->lora_t) {
+        if (!a->lora_b || a->lora_r <= 0 || (a->lora_r % 8) || (a->ldt % 8) || (a->ldb % 8))
+            return set_error(S2V_E_BADARG, "s2v_linear: bad LoRA operands");
+        const int gn = a->lora_group_n > 0 ? a->lora_group_n : a->N;
+        if (gn % 128 && gn != a->N) return set_error(S2V_E_UNSUPPORTED, "s2v_linear: lora_group_n must be a multiple of 128");
+    }
+    if (a->epilogue == S2V_EPI_GATE_RESIDUAL && !a->mod) return set_error(S2V_E_BADARG, "s2v_linear: gate table missing");
+    int rc = ensure_device();
+    if (rc) return rc;
+    // 256-wide tiles for the big projections, 128-wide when N is small or a LoRA group boundary is not 256-aligned
+    const int gn = (a->lora_t && a->lora_group_n > 0) ? a->lora_group_n : a->N;
+    const bool wide = (a->N >= 256) && (gn % 256 == 0 || !a->lora_t || gn == a->N);
+    switch (a->epilogue) {
+        case S2V_EPI_BIAS:
+            return wide ? launch_gemm<256, S2V_EPI_BIAS>(a, stream) : launch_gemm<128, S2V_EPI_BIAS>(a, stream);
+        case S2V_EPI_BIAS_GELU:
+            return wide ? launch_gemm<256, S2V_EPI_BIAS_GELU>(a, stream) : launch_gemm<128, S2V_EPI_BIAS_GELU>(a, stream);
+        case S2V_EPI_GATE_RESIDUAL:
+            return wide ? launch_gemm<256, S2V_EPI_GATE_RESIDUAL>(a, stream)
+                        : launch_gemm<128, S2V_EPI_GATE_RESIDUAL>(a, stream);
+        default:
+            return set_error(S2V_E_BADARG, "s2v_linear: unknown epilogue");
+    }
+}
+
+extern "C" int s2v_qkv_lora(const s2v_linear_args* a, void* stream) { return s2v_linear(a, stream); }
+extern "C" int s2v_outproj_lora_gate_residual(const s2v_linear_args* a, void* stream) {
+    if (a && a->epilogue != S2V_EPI_GATE_RESIDUAL) return set_error(S2V_E_BADARG, "outproj: epilogue must be GATE_RESIDUAL");
+    return s2v_linear(a, stream);
+}
+extern "C" int s2v_ffn_up_gelu_lora(const s2v_linear_args* a, void* stream) {
+    if (a && a->epilogue != S2V_EPI_BIAS_GELU) return set_error(S2V_E_BADARG, "ffn_up: epilogue must be BIAS_GELU");
+    return s2v_linear(a, stream);
+}
+extern "C" int s2v_ffn_down_lora_gate_residual(const s2v_linear_args* a, void* stream) {
+    if (a && a->epilogue != S2V_EPI_GATE_RESIDUAL) return set_error(S2V_E_BADARG, "ffn_down: epilogue must be GATE_RESIDUAL");
+    return s2v_linear(a, stream);
+}

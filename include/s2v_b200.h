@@ -1,0 +1,171 @@
+/*
+ * s2v_b200 — C ABI of the B200-native (sm_100a) kernels behind the CogVideoX subject-to-video denoising loop.
+ *
+ * The reference (carpedkm/disentangled-subject-to-vid) is pure Python on a diffusers fork and has NO native FFI;
+ * each entry point below replaces the group of PyTorch library calls named in its comment (file:line under
+ * /root/reference, S/ = src/, D/ = diffusers/src/diffusers/).  INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; bf16 = 16-bit brain float; row-major;
+ *     `ld*` are leading dimensions in ELEMENTS;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library allocates nothing and keeps no
+ *     tensor state; all launches go to `stream` (a cudaStream_t passed as void*), are asynchronous, do not
+ *     synchronise the host and are CUDA-graph-capture safe;
+ *   - return value: 0 = ok, negative = bad argument / unsupported shape (S2V_E_*), positive = cudaError_t.
+ *     Nothing throws or exits across the ABI; s2v_last_error() returns a thread-local description.
+ *   - there is no CPU fallback and no other backend: on a machine without an sm_100 device every compute
+ *     entry point returns S2V_E_NO_DEVICE.
+ *
+ * Token layout: every activation of the transformer is ONE buffer [B, S, D] with rows ordered
+ * [text (L) | reference image (n_ref) | video (F*n)] — the order of the reference's joint attention
+ * (D/models/attention_processor.py:2039), so its torch.cat / split copies disappear.
+ */
+#ifndef S2V_B200_H
+#define S2V_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2V_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define S2V_API __attribute__((visibility("default")))
+#else
+#define S2V_API
+#endif
+
+#define S2V_E_BADARG (-1)
+#define S2V_E_UNSUPPORTED (-2)
+#define S2V_E_NO_DEVICE (-3)
+#define S2V_E_DRIVER (-4)
+
+/* epilogues of s2v_linear */
+#define S2V_EPI_BIAS 0          /* out = bf16(alpha*acc + bias)                                   */
+#define S2V_EPI_BIAS_GELU 1     /* out = bf16(gelu_tanh(acc + bias))                              */
+#define S2V_EPI_GATE_RESIDUAL 2 /* out = bf16(out + gate[batch(row), seg(row), col]*(acc + bias)) */
+
+S2V_API int s2v_abi_version(void);
+S2V_API const char* s2v_last_error(void);
+/* 0 if device `dev` is sm_100 (B200); S2V_E_NO_DEVICE otherwise. */
+S2V_API int s2v_device_check(int dev);
+
+/* ------------------------------------------------------------------------------------------------ linear + LoRA
+ * y[M,N] = x[M,K] * w[N,K]^T (+ bias) (+ lora_t[M, g*r : (g+1)*r] * lora_b[N, r]^T), tcgen05 + TMA, fp32 accumulate,
+ * with a fused epilogue.  `lora_t` is the already down-projected and scaled activation  s * x * A^T  (a first
+ * s2v_linear call with alpha = s and w = A); the up-projection B rides along as `lora_r` extra K columns of the main
+ * GEMM, so the LoRA update costs no extra pass over y.  g = (column / lora_group_n) lets q/k/v share one call.
+ * Replaces: nn.Linear + peft lora.Linear at D/models/attention_processor.py:2049-2051,2090 (to_q/to_k/to_v/to_out),
+ * D/models/attention.py:1241-1242 (ff.net.0.proj, ff.net.2), D/models/embeddings.py:411,416 (text_proj, proj),
+ * cogvideox_transformer_3d.py:543 (proj_out); GELU-tanh of D/models/activations.py:88-89; the gated residual adds of
+ * cogvideox_transformer_3d.py:165-167,182-184.
+ */
+typedef struct {
+    const void* x;      int64_t ldx;   /* [M,K] bf16 */
+    const void* w;      int64_t ldw;   /* [N,K] bf16 */
+    const void* bias;                  /* [N] bf16 or NULL */
+    const void* lora_t; int64_t ldt;   /* [M, groups*lora_r] bf16 or NULL */
+    const void* lora_b; int64_t ldb;   /* [N, lora_r] bf16 */
+    int32_t lora_r;                    /* 0 = no LoRA; multiple of 8 */
+    int32_t lora_group_n;              /* columns per LoRA group (N if a single group) */
+    void* out;          int64_t ldo;   /* [M,N] bf16 (read-modify-write for GATE_RESIDUAL) */
+    int32_t M, N, K;                   /* K multiple of 8 */
+    int32_t epilogue;                  /* S2V_EPI_* */
+    float alpha;
+    /* GATE_RESIDUAL only: modulation table [B, mod_stride] fp32; gate vector for a row is
+       mod + batch*mod_stride + (seq < text_len ? gate_off_text : gate_off_other), batch = row / rows_per_batch */
+    const float* mod;   int32_t mod_stride, gate_off_text, gate_off_other, rows_per_batch, text_len;
+} s2v_linear_args;
+S2V_API int s2v_linear(const s2v_linear_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ joint attention
+ * o[b, s, h*64:(h+1)*64] = softmax(q k^T / 8) v over ALL S rows (text|ref|video), no mask, head_dim 64.
+ * qkv is the fused projection output [B, S, 3*H*64] bf16 (q | k | v along the last dim, heads contiguous);
+ * o is [B, S, H*64] bf16 — directly the A operand of the out-projection.  tcgen05 flash attention: S and P live in
+ * TMEM, K/V tiles are staged by TMA, fp32 online softmax.
+ * Replaces F.scaled_dot_product_attention + the two transposes at D/models/attention_processor.py:2056-2058,2083-2088.
+ */
+S2V_API int s2v_attn_fwd(const void* qkv, void* o, int32_t B, int32_t S, int32_t H, float softmax_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ AdaLN-Zero
+ * out[b,s,:] = LayerNorm_D(x[b,s,:]; w, bias, eps) * (1 + scale) + shift, where (shift, scale) come from the
+ * modulation table mod[B, mod_stride] fp32 at offsets (shift_off_text, scale_off_text) for s < text_len and
+ * (shift_off_other, scale_off_other) otherwise.  CogVideoXLayerNormZero (D/models/normalization.py:479-482): video and
+ * reference rows share chunks 0/1, text rows use chunks 3/4 (the `enable_lora` context there is a no-op).
+ */
+S2V_API int s2v_adaln_modulate(const void* x, void* out, const void* ln_w, const void* ln_b, const float* mod,
+                       int32_t mod_stride, int32_t shift_off_text, int32_t scale_off_text, int32_t shift_off_other,
+                       int32_t scale_off_other, int32_t B, int32_t S, int32_t D, int32_t text_len, float eps,
+                       void* stream);
+
+/* Final norms: out = LN2(LN1(x)) * (1 + scale) + shift on rows [row0, S) of every batch, written densely as
+ * [B, S-row0, D].  nn.LayerNorm norm_final + AdaLayerNorm norm_out (cogvideox_transformer_3d.py:536-542,
+ * D/models/normalization.py:70-81: chunk order shift, scale). */
+S2V_API int s2v_final_norm(const void* x, void* out, const void* ln1_w, const void* ln1_b, const void* ln2_w,
+                   const void* ln2_b, const float* mod, int32_t mod_stride, int32_t shift_off, int32_t scale_off,
+                   int32_t B, int32_t S, int32_t row0, int32_t D, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ q/k LayerNorm + RoPE
+ * In place on the q and k thirds of qkv [B, S, 3*H*64]: per-head LayerNorm(64, eps, affine shared across heads), then
+ * for rows s >= text_len the interleaved-pair rotation out = x*cos + rot(x)*sin with table row (s - text_len) of
+ * cos/sin [S - text_len, 64] fp32 (reference-image rows first, then video rows — the order of the pipeline's table,
+ * S/custom_cogvideox_pipe.py:228-235).  cos == NULL skips RoPE (CogVideoX-2B).
+ * Replaces attn.norm_q / norm_k and apply_rotary_emb (D/models/attention_processor.py:2060-2080,
+ * D/models/embeddings.py:759-778). */
+S2V_API int s2v_qk_norm_rope(void* qkv, const void* nq_w, const void* nq_b, const void* nk_w, const void* nk_b,
+                     const float* cos, const float* sin, int32_t B, int32_t S, int32_t H, int32_t text_len, float eps,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------ small-batch linear
+ * out[b,n] = beta*out[b,n] + alpha*(sum_k w[n,k]*f(x[b,k]) + bias[n]),  f = identity (act_in=0) or SiLU (act_in=1);
+ * x/out fp32, w/bias bf16, B <= 8.  Used for the timestep MLP (D/models/embeddings.py:860-875), the 6*D AdaLN
+ * modulation vectors (D/models/normalization.py:473-476) incl. their LoRA pair, and norm_out.linear. */
+S2V_API int s2v_small_linear(const float* x, int64_t ldx, const void* w, int64_t ldw, const void* bias, float* out,
+                     int64_t ldo, int32_t B, int32_t N, int32_t K, int32_t act_in, float alpha, float beta,
+                     int32_t round_bf16, void* stream);
+
+/* Sinusoidal timestep embedding, flip_sin_to_cos=True, freq_shift=0 (D/models/embeddings.py:27-78): out[b, 0:D/2] =
+ * cos(t_b * f_i), out[b, D/2:] = sin(t_b * f_i), f_i = exp(-ln(10000) * i / (D/2)); rounded through bf16 when
+ * round_bf16 (cogvideox_transformer_3d.py:490). */
+S2V_API int s2v_timestep_sinusoid(const float* t, float* out, int32_t B, int32_t D, int32_t round_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ patchify / unpatchify
+ * patchify: latents [NB, C, H, W] bf16 -> rows [NB*(H/p)*(W/p), C*p*p] bf16 (k = c*p*p + dy*p + dx), the im2col of
+ * the k=p, stride=p Conv2d patch embedding (D/models/embeddings.py:414-419); the conv itself is an s2v_linear call.
+ * unpatchify: tokens [NB, (H/p)*(W/p), C*p*p] bf16 -> [NB, C, H, W] bf16 (cogvideox_transformer_3d.py:549-551). */
+S2V_API int s2v_patchify(const void* latents, void* rows, int32_t NB, int32_t C, int32_t H, int32_t W, int32_t p, void* stream);
+S2V_API int s2v_unpatchify(const void* tokens, void* latents, int32_t NB, int32_t C, int32_t H, int32_t W, int32_t p,
+                   void* stream);
+
+/* dst[b, row0 + r, :] += table[r, :] for r < R (bf16; CogVideoX-2B sincos positional embedding on the video rows,
+ * D/models/embeddings.py:433-446). */
+S2V_API int s2v_add_rows(void* dst, const void* table, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t R, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ CFG + DDIM step
+ * latents' = bf16( a*x + b*( sa*x - sb*v ) ),  v = u + g*(t - u) in fp32 from noise_pred [2P, n] bf16 (uncond first),
+ * with the reference's rounding points: sa*x and a*x are rounded to bf16 before they meet fp32 terms, every fp32
+ * op is individually rounded (no FMA contraction) — bit-exact with S/custom_cogvideox_pipe.py:266-296 +
+ * D/schedulers/scheduling_ddim_cogvideox.py:383-394.  The four coefficients are computed by the host in fp64 exactly
+ * as the reference and passed as fp32.  x0_out (fp32, optional) receives pred_original_sample. */
+S2V_API int s2v_cfg_ddim_step(const void* noise_pred, const void* latents, void* latents_out, float* x0_out, int64_t n_per_half,
+                      float guidance, float sqrt_alpha, float sqrt_beta, float a_coef, float b_coef, void* stream);
+
+/* Plain DDIM v-prediction step on an fp32 model output and a bf16 sample (the scheduler.step() surface,
+ * D/schedulers/scheduling_ddim_cogvideox.py:365-394): prev_out, x0_out fp32, same rounding points as above. */
+S2V_API int s2v_ddim_step(const float* model_output, const void* sample, float* prev_out, float* x0_out, int64_t n,
+                          float sqrt_alpha, float sqrt_beta, float a_coef, float b_coef, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ stage wrappers
+ * Thin named entry points (the per-stage ABI proposed in SURVEY.md §8b); each forwards to s2v_linear. */
+S2V_API int s2v_qkv_lora(const s2v_linear_args* a, void* stream);                     /* K1: to_q|to_k|to_v + LoRA, bias      */
+S2V_API int s2v_outproj_lora_gate_residual(const s2v_linear_args* a, void* stream);   /* K5+K8                                */
+S2V_API int s2v_ffn_up_gelu_lora(const s2v_linear_args* a, void* stream);             /* K10 first half                       */
+S2V_API int s2v_ffn_down_lora_gate_residual(const s2v_linear_args* a, void* stream);  /* K10 second half + K8                 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2V_B200_H */

@@ -1,0 +1,279 @@
+"""Kernel bring-up on a real B200: every kernel of libs2v_b200.so against plain torch (fp32 math on the same bf16
+inputs), one subprocess per group with a timeout so that a hung kernel cannot take the box down.
+
+    python tools/bringup.py            # all groups
+    python tools/bringup.py gemm attn  # selected groups
+
+Writes gpurun_out/bringup_<group>.log.  Not part of the product or of the test-suite; it is the first thing run on
+the GPU after a kernel change.
+"""
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def _sync_time(fn, iters=5, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(iters):
+        fn()
+    ev1.record()
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) / iters
+
+
+def report(name, got, ref, tol):
+    import torch
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs().max().item()
+    den = ref.abs().max().item() + 1e-12
+    bad = not math.isfinite(err) or err / den > tol
+    print(json.dumps({"test": name, "max_abs_err": err, "ref_max": den, "rel": err / den, "ok": not bad}), flush=True)
+    return not bad
+
+
+def group_gemm():
+    import torch
+    from s2v_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+
+    def mk(*shape, s=1.0):
+        return (torch.randn(*shape, device=dev) * s).to(torch.bfloat16)
+
+    for (M, N, K, bias) in [(128, 128, 64, False), (128, 256, 64, False), (256, 256, 128, True), (300, 384, 512, True),
+                            (1000, 3072, 3072, True), (4276, 1920, 1920, True), (130, 64, 256, True)]:
+        x, w = mk(M, K), mk(N, K, s=0.05)
+        b = mk(N) if bias else None
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ops.linear(x, w, b, out)
+        torch.cuda.synchronize()
+        ref = x.float() @ w.float().t() + (b.float() if bias else 0)
+        ok &= report(f"gemm_bias M{M} N{N} K{K}", out, ref, 1e-2)
+    # GELU
+    M, N, K = 777, 512, 256
+    x, w, b = mk(M, K), mk(N, K, s=0.1), mk(N)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.linear(x, w, b, out, epilogue=ops.EPI_BIAS_GELU)
+    ref = torch.nn.functional.gelu(x.float() @ w.float().t() + b.float(), approximate="tanh")
+    ok &= report("gemm_gelu", out, ref, 1e-2)
+    # alpha
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.linear(x, w, None, out, alpha=0.5)
+    ok &= report("gemm_alpha", out, 0.5 * (x.float() @ w.float().t()), 1e-2)
+    # LoRA (extended K), grouped
+    for (M, N, K, r, gn) in [(500, 768, 256, 128, 256), (500, 768, 256, 8, 256), (300, 384, 128, 16, 128), (260, 512, 192, 64, 0)]:
+        groups = (N // gn) if gn else 1
+        x, w, b = mk(M, K), mk(N, K, s=0.05), mk(N)
+        t, lb = mk(M, groups * r), mk(N, r, s=0.1)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ops.linear(x, w, b, out, lora_t=t, lora_b=lb, lora_group_n=gn)
+        ref = x.float() @ w.float().t() + b.float()
+        g = gn or N
+        for gi in range(groups):
+            ref[:, gi * g:(gi + 1) * g] += t[:, gi * r:(gi + 1) * r].float() @ lb[gi * g:(gi + 1) * g].float().t()
+        ok &= report(f"gemm_lora M{M} N{N} K{K} r{r} gn{gn}", out, ref, 1e-2)
+    # gate residual: 2 batches, text rows use another gate
+    B, S, D, K, L = 2, 333, 256, 128, 50
+    x, w, b = mk(B * S, K), mk(D, K, s=0.1), mk(D)
+    res = mk(B, S, D)
+    mod = torch.randn(B, 6 * D, device=dev)
+    out = res.clone()
+    ops.linear(x, w, b, out.view(B * S, D), epilogue=ops.EPI_GATE_RESIDUAL, mod=mod, gate_off_text=5 * D, gate_off_other=2 * D,
+               rows_per_batch=S, text_len=L)
+    y = (x.float() @ w.float().t() + b.float()).view(B, S, D)
+    gate = torch.where((torch.arange(S, device=dev) < L)[None, :, None], mod[:, None, 5 * D:6 * D], mod[:, None, 2 * D:3 * D])
+    ok &= report("gemm_gate_residual", out, res.float() + gate * y, 1e-2)
+    # strided output (column slice of a wider buffer) and strided input
+    M, N, K = 200, 128, 64
+    big = torch.zeros(M, 512, device=dev, dtype=torch.bfloat16)
+    xw = mk(M, 256)
+    w = mk(N, K, s=0.1)
+    ops.linear(xw[:, 64:128], w, None, big[:, 128:256])
+    ok &= report("gemm_strided", big[:, 128:256], xw[:, 64:128].float() @ w.float().t(), 1e-2)
+    ok &= report("gemm_strided_untouched", big[:, :128], torch.zeros(M, 128, device=dev), 1e-9) if False else ok
+    # timing at the cfg-3 shapes
+    for (M, N, K, tag) in [(38252, 9216, 3072, "qkv"), (38252, 3072, 3072, "out"), (38252, 12288, 3072, "ffn_up"),
+                           (38252, 3072, 12288, "ffn_down")]:
+        x, w, b = mk(M, K), mk(N, K, s=0.02), mk(N)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ms = _sync_time(lambda: ops.linear(x, w, b, out))
+        ms_t = _sync_time(lambda: torch.nn.functional.linear(x, w, b))
+        print(json.dumps({"bench": f"gemm_{tag}", "ms": ms, "tflops": 2 * M * N * K / ms / 1e9, "torch_ms": ms_t,
+                          "torch_tflops": 2 * M * N * K / ms_t / 1e9}), flush=True)
+        idx = torch.randint(0, M, (64,), device=dev)
+        ok &= report(f"gemm_big_{tag}_rows", out[idx], x[idx].float() @ w.float().t() + b.float(), 1e-2)
+    return ok
+
+
+def group_attn():
+    import torch
+    import torch.nn.functional as F
+    from s2v_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+    for (B, S, H, scale_in) in [(1, 128, 1, 1.0), (1, 256, 1, 1.0), (1, 256, 2, 1.0), (2, 354, 2, 1.0), (1, 1000, 3, 1.0),
+                                (1, 640, 2, 6.0), (2, 4276, 2, 1.0)]:
+        qkv = (torch.randn(B, S, 3 * H * 64, device=dev) * scale_in).to(torch.bfloat16)
+        out = torch.full((B, S, H * 64), float("nan"), device=dev, dtype=torch.bfloat16)
+        ops.attention(qkv, out, H)
+        torch.cuda.synchronize()
+        q, k, v = [t.view(B, S, H, 64).transpose(1, 2).float() for t in qkv.chunk(3, dim=-1)]
+        ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
+        ok &= report(f"attn B{B} S{S} H{H} x{scale_in}", out, ref, 2e-2)
+    B, S, H = 2, 19126, 48
+    qkv = torch.randn(B, S, 3 * H * 64, device=dev).to(torch.bfloat16)
+    out = torch.empty(B, S, H * 64, device=dev, dtype=torch.bfloat16)
+    ms = _sync_time(lambda: ops.attention(qkv, out, H), iters=3, warm=1)
+    q, k, v = [t.view(B, S, H, 64).transpose(1, 2) for t in qkv.chunk(3, dim=-1)]
+    ms_t = _sync_time(lambda: F.scaled_dot_product_attention(q, k, v), iters=3, warm=1)
+    fl = 4.0 * B * H * S * S * 64
+    print(json.dumps({"bench": "attn_cfg3", "ms": ms, "tflops": fl / ms / 1e9, "torch_sdpa_ms": ms_t,
+                      "torch_tflops": fl / ms_t / 1e9}), flush=True)
+    ref = F.scaled_dot_product_attention(q[:, :4, :2048].float(), k[:, :4].float(), v[:, :4].float())
+    ok &= report("attn_big_slice", out.view(B, S, H, 64)[:, :2048, :4].transpose(1, 2), ref, 2e-2)
+    return ok
+
+
+def group_elementwise():
+    import torch
+    import torch.nn.functional as F
+    from s2v_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+    bf = torch.bfloat16
+    for (B, S, D, L) in [(2, 354, 1920, 226), (2, 354, 3072, 226), (1, 77, 128, 10), (2, 100, 4096, 0)]:
+        x = torch.randn(B, S, D, device=dev).to(bf)
+        w = (1 + 0.1 * torch.randn(D, device=dev)).to(bf)
+        b = (0.1 * torch.randn(D, device=dev)).to(bf)
+        mod = torch.randn(B, 6 * D, device=dev)
+        out = torch.empty_like(x)
+        ops.adaln_modulate(x, out, w, b, mod, shift_off_text=3 * D, scale_off_text=4 * D, shift_off_other=0, scale_off_other=D,
+                           text_len=L, eps=1e-5)
+        ln = F.layer_norm(x.float(), (D,), w.float(), b.float(), 1e-5)
+        is_text = (torch.arange(S, device=dev) < L)[None, :, None]
+        shift = torch.where(is_text, mod[:, None, 3 * D:4 * D], mod[:, None, 0:D])
+        scale = torch.where(is_text, mod[:, None, 4 * D:5 * D], mod[:, None, D:2 * D])
+        ok &= report(f"adaln B{B} S{S} D{D}", out, ln * (1 + scale) + shift, 1e-2)
+        # final norm
+        row0 = L
+        if S - row0 > 0:
+            w2 = (1 + 0.1 * torch.randn(D, device=dev)).to(bf)
+            b2 = (0.1 * torch.randn(D, device=dev)).to(bf)
+            out2 = torch.empty(B, S - row0, D, device=dev, dtype=bf)
+            ops.final_norm(x, out2, w, b, w2, b2, mod, shift_off=0, scale_off=D, row0=row0, eps=1e-5)
+            l1 = F.layer_norm(x[:, row0:].float(), (D,), w.float(), b.float(), 1e-5).to(bf).float()
+            l2 = F.layer_norm(l1, (D,), w2.float(), b2.float(), 1e-5)
+            ok &= report(f"final_norm D{D}", out2, l2 * (1 + mod[:, None, D:2 * D]) + mod[:, None, 0:D], 1e-2)
+    # qk norm + rope
+    for (B, S, H, L, rope) in [(2, 354, 30, 226, True), (1, 200, 48, 100, True), (2, 99, 2, 20, False)]:
+        qkv = torch.randn(B, S, 3 * H * 64, device=dev).to(bf)
+        nqw, nkw = [(1 + 0.1 * torch.randn(64, device=dev)).to(bf) for _ in range(2)]
+        nqb, nkb = [(0.1 * torch.randn(64, device=dev)).to(bf) for _ in range(2)]
+        ang = torch.rand(S - L, 32, device=dev) * 6.28
+        cos = ang.cos().repeat_interleave(2, dim=1).contiguous()
+        sin = ang.sin().repeat_interleave(2, dim=1).contiguous()
+        ref = qkv.clone().float().view(B, S, 3, H, 64)
+        got = qkv.clone()
+        ops.qk_norm_rope(got, nqw, nqb, nkw, nkb, cos if rope else None, sin if rope else None, H, L)
+        for i, (w_, b_) in enumerate(((nqw, nqb), (nkw, nkb))):
+            t = F.layer_norm(ref[:, :, i], (64,), w_.float(), b_.float(), 1e-6)
+            if rope:
+                tr = t[:, L:].to(bf).float()
+                xr, xi = tr.reshape(B, S - L, H, 32, 2).unbind(-1)
+                rot = torch.stack([-xi, xr], dim=-1).flatten(3)
+                t = torch.cat([t[:, :L], tr * cos[None, :, None] + rot * sin[None, :, None]], dim=1)
+            ref[:, :, i] = t
+        ok &= report(f"qk_norm_rope B{B} S{S} H{H} rope{rope}", got, ref.view(B, S, -1), 1e-2)
+    # small linear
+    x = torch.randn(2, 512, device=dev)
+    w = (0.05 * torch.randn(18432, 512, device=dev)).to(bf)
+    b = (0.05 * torch.randn(18432, device=dev)).to(bf)
+    out = torch.zeros(2, 18432, device=dev)
+    ops.small_linear(x, w, b, out, act_in=1)
+    ok &= report("small_linear_silu", out, F.silu(x) @ w.float().t() + b.float(), 1e-4)
+    out2 = out.clone()
+    ops.small_linear(x, w, None, out2, alpha=0.5, beta=1.0)
+    ok &= report("small_linear_accum", out2, out + 0.5 * (x @ w.float().t()), 1e-4)
+    # timestep sinusoid
+    t = torch.tensor([999.0, 19.0], device=dev)
+    o = torch.empty(2, 3072, device=dev)
+    ops.timestep_sinusoid(t, o)
+    half = 1536
+    e = torch.exp(-math.log(10000) * torch.arange(half, device=dev, dtype=torch.float32) / half)
+    arg = t[:, None] * e[None]
+    ok &= report("timestep_sinusoid", o, torch.cat([arg.cos(), arg.sin()], dim=-1), 1e-5)
+    # patchify / unpatchify
+    lat = torch.randn(6, 16, 60, 90, device=dev).to(bf)
+    rows = torch.empty(6 * 30 * 45, 64, device=dev, dtype=bf)
+    ops.patchify(lat, rows, 2)
+    ref = lat.view(6, 16, 30, 2, 45, 2).permute(0, 2, 4, 1, 3, 5).reshape(-1, 64)
+    ok &= report("patchify", rows, ref, 0)
+    back = torch.empty_like(lat)
+    ops.unpatchify(rows.view(6, 1350, 64), back, 2)
+    ok &= report("unpatchify_roundtrip", back, lat, 0)
+    # add rows
+    dst = torch.randn(2, 50, 128, device=dev).to(bf)
+    tab = torch.randn(30, 128, device=dev).to(bf)
+    want = dst.clone().float()
+    want[:, 20:50] += tab.float()
+    ops.add_rows(dst, tab, 20)
+    ok &= report("add_rows", dst, want.to(bf), 1e-9)
+    # cfg + ddim, bit-exact against the same expression evaluated by torch CUDA ops with fp32 scalars
+    n = 13 * 16 * 60 * 90
+    noise = torch.randn(2, n, device=dev).to(bf)
+    lat = torch.randn(1, n, device=dev).to(bf)
+    outl = torch.empty_like(lat)
+    x0 = torch.empty(1, n, device=dev)
+    g, sa, sb, a, b_ = 6.0, 0.9412, 0.3377, 0.97531, 0.02345
+    ops.cfg_ddim_step(noise, lat, outl, g, sa, sb, a, b_, x0_out=x0)
+    u, t_ = noise.float().chunk(2)
+    v = u + g * (t_ - u)
+    x0_ref = (torch.tensor(sa, dtype=torch.float64) * lat) - torch.tensor(sb, dtype=torch.float64) * v
+    prev = torch.tensor(a, dtype=torch.float64) * lat + torch.tensor(b_, dtype=torch.float64) * x0_ref
+    print(json.dumps({"test": "cfg_ddim_bitexact_vs_torch_cuda", "x0_equal": bool(torch.equal(x0, x0_ref)),
+                      "prev_equal": bool(torch.equal(outl, prev.to(bf))), "x0_dtype": str(x0_ref.dtype)}), flush=True)
+    ok &= bool(torch.equal(outl, prev.to(bf)))
+    return ok
+
+
+GROUPS = {"gemm": group_gemm, "attn": group_attn, "elementwise": group_elementwise}
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--child":
+        import s2v_b200  # noqa: F401
+        t0 = time.time()
+        ok = GROUPS[sys.argv[2]]()
+        print(json.dumps({"group": sys.argv[2], "ok": bool(ok), "seconds": time.time() - t0}), flush=True)
+        sys.exit(0 if ok else 1)
+    os.makedirs(OUT, exist_ok=True)
+    groups = sys.argv[1:] or list(GROUPS)
+    rc = 0
+    for g in groups:
+        log = os.path.join(OUT, f"bringup_{g}.log")
+        with open(log, "w") as f:
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", g], stdout=f, stderr=subprocess.STDOUT,
+                                   timeout=int(os.environ.get("BRINGUP_TIMEOUT", "300")))
+                code = r.returncode
+            except subprocess.TimeoutExpired:
+                code = -999
+                f.write("\nTIMEOUT (kernel hang?)\n")
+        print(f"== {g}: exit {code}")
+        print(open(log).read()[-6000:])
+        rc |= (code != 0)
+    sys.exit(rc)
