@@ -3,7 +3,24 @@ denoising hot path of carpedkm/disentangled-subject-to-vid, behind the reference
 
 The directory name is not a Python identifier; import it as `s2v_b200` (the alias module at the repo root) or with
 importlib.import_module("disentangled-subject-to-vid_b200").
-"""
-from . import _lib, ops  # noqa: F401
 
-__all__ = ["_lib", "ops"]
+    csrc/ + include/s2v_b200.h   hand-written sm_100a kernels (tcgen05 / TMEM / TMA) behind a C ABI
+    ops                          ctypes wrappers: torch tensors -> raw pointers
+    engine                       weight packing, workspaces, the fused block / model forward
+    modules, pipeline, scheduler the reference's operator surface (same names, arguments, errors)
+    lora                         PEFT-layout LoRA adapters, read in place
+    parallel                     prompt / CFG sharding over the GPUs of one node (torch.distributed)
+"""
+from . import _lib, engine, lora, modules, ops, parallel, pipeline, scheduler, tables  # noqa: F401
+from .lora import inject_lora, load_lora_state_dict  # noqa: F401
+from .modules import (  # noqa: F401
+    Attention,
+    CogVideoXAttnProcessor2_0,
+    CogVideoXBlock,
+    CogVideoXTransformer3DModel,
+    attach,
+)
+from .pipeline import CogVideoXPipelineOutput, CustomCogVideoXPipeline  # noqa: F401
+from .scheduler import CogVideoXDDIMScheduler  # noqa: F401
+
+__version__ = "0.1.0"

@@ -48,7 +48,7 @@ SIGNATURES = {
     "s2v_final_norm": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_qk_norm_rope": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_small_linear": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _vp],
-    "s2v_timestep_sinusoid": [_vp, _vp, _i32, _i32, _i32, _vp],
+    "s2v_timestep_sinusoid": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "s2v_patchify": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "s2v_unpatchify": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "s2v_add_rows": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -80,7 +80,12 @@ def load() -> C.CDLL:
     return _lib
 
 
+launch_count = 0  # kernels launched through the C ABI by this process (every compute entry point launches exactly one)
+
+
 def check(rc: int, what: str):
+    global launch_count
+    launch_count += 1
     if rc != 0:
         msg = load().s2v_last_error().decode("utf-8", "replace")
         kind = "invalid argument / unsupported" if rc < 0 else "CUDA error"

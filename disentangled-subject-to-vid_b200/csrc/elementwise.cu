@@ -273,13 +273,13 @@ small_linear_kernel(const float* __restrict__ x, long long ldx, const bf16* __re
     }
 }
 
-__global__ void timestep_sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int D, int round_bf16) {
+__global__ void timestep_sinusoid_kernel(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ out,
+                                         int B, int D, int round_bf16) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = D / 2;
     if (idx >= B * half) return;
     const int b = idx / half, i = idx - b * half;
-    const float exponent = (-9.210340371976184f * float(i)) / float(half);   // -ln(10000) * i / half  (fp32, as the reference)
-    const float arg = t[b] * expf(exponent);
+    const float arg = __fmul_rn(t[b], freqs[i]);   // freqs = exp(-ln(10000) * i / half), tabulated by the host in fp32
     float c = cosf(arg), s = sinf(arg);
     if (round_bf16) {
         c = __bfloat162float(__float2bfloat16(c));
@@ -450,11 +450,12 @@ extern "C" int s2v_small_linear(const float* x, int64_t ldx, const void* w, int6
     return check_launch("small_linear_kernel");
 }
 
-extern "C" int s2v_timestep_sinusoid(const float* t, float* out, int32_t B, int32_t D, int32_t round_bf16, void* stream_) {
-    if (!t || !out || B <= 0 || D <= 0 || (D % 2)) return set_error(S2V_E_BADARG, "s2v_timestep_sinusoid: bad argument");
+extern "C" int s2v_timestep_sinusoid(const float* t, const float* freqs, float* out, int32_t B, int32_t D, int32_t round_bf16,
+                                     void* stream_) {
+    if (!t || !freqs || !out || B <= 0 || D <= 0 || (D % 2)) return set_error(S2V_E_BADARG, "s2v_timestep_sinusoid: bad argument");
     S2V_PROLOGUE();
     const int n = B * (D / 2);
-    timestep_sinusoid_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, out, B, D, round_bf16);
+    timestep_sinusoid_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, freqs, out, B, D, round_bf16);
     return check_launch("timestep_sinusoid_kernel");
 }
 

@@ -224,6 +224,10 @@ class TransformerEngine:
         self.rotary = bool(g("use_rotary_positional_embeddings", False))
         self.spatial_scale = float(g("spatial_interpolation_scale", 1.875))
         self.temporal_scale = float(g("temporal_interpolation_scale", 1.0))
+        self.freq_shift = float(g("freq_shift", 0) or 0)
+        if not bool(g("flip_sin_to_cos", True)):
+            raise RuntimeError("only flip_sin_to_cos=True (CogVideoX) is implemented")
+        self._freqs = None
         self.model = model
         self.merge_lora = merge_lora
         self.device = next(model.parameters()).device
@@ -269,7 +273,9 @@ class TransformerEngine:
             t = t.expand(B)
         t = t.contiguous()
         sin = torch.empty(B, self.D, device=self.device, dtype=torch.float32)
-        ops.timestep_sinusoid(t, sin)
+        if self._freqs is None:
+            self._freqs = ops.timestep_freqs(self.D, self.device, self.freq_shift)
+        ops.timestep_sinusoid(t, self._freqs, sin)
         h1 = torch.empty(B, self.time_dim, device=self.device, dtype=torch.float32)
         ops.small_linear(sin, self.t1.w, self.t1.b, h1)
         emb = torch.empty(B, self.t2.w.shape[0], device=self.device, dtype=torch.float32)

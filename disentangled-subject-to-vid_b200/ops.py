@@ -20,6 +20,50 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """Optional per-kernel CUDA-event timing on the launching stream (used by bench.py for the live roofline figure).
+    Events are recorded around every launch whose tag is in `names`; nothing synchronises until `summary()`."""
+
+    def __init__(self, names):
+        self.names = set(names)
+        self.events = {n: [] for n in self.names}
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for n, evs in self.events.items():
+            if evs:
+                ms = [a.elapsed_time(b) for a, b in evs]
+                out[n] = {"launches": len(ms), "avg_ms": sum(ms) / len(ms), "total_ms": sum(ms)}
+        return out
+
+
+_PROF: Optional[KernelTimer] = None
+
+
+def set_kernel_timer(t: Optional[KernelTimer]):
+    global _PROF
+    _PROF = t
+
+
+class _timed:
+    def __init__(self, tag):
+        self.on = _PROF is not None and tag in _PROF.names
+        self.tag = tag
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _PROF.events[self.tag].append((self.e0, e1))
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -92,7 +136,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: 
         a.mod, a.mod_stride = None, 0
     a.gate_off_text, a.gate_off_other, a.rows_per_batch, a.text_len = gate_off_text, gate_off_other, rows_per_batch, text_len
     lib = _lib.load()
-    _lib.check(getattr(lib, entry)(C.byref(a), _stream()), entry)
+    with _timed(entry):
+        _lib.check(getattr(lib, entry)(C.byref(a), _stream()), entry)
     return out
 
 
@@ -104,8 +149,9 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, heads: int, scale: Optional[
     if W != 3 * heads * 64 or not qkv.is_contiguous() or not out.is_contiguous() or tuple(out.shape) != (B, S, heads * 64):
         raise RuntimeError("attention: expected contiguous qkv [B,S,3*H*64] and out [B,S,H*64]")
     lib = _lib.load()
-    _lib.check(lib.s2v_attn_fwd(qkv.data_ptr(), out.data_ptr(), B, S, heads, scale if scale is not None else 0.125, _stream()),
-               "s2v_attn_fwd")
+    with _timed("s2v_attn_fwd"):
+        _lib.check(lib.s2v_attn_fwd(qkv.data_ptr(), out.data_ptr(), B, S, heads, scale if scale is not None else 0.125, _stream()),
+                   "s2v_attn_fwd")
     return out
 
 
@@ -165,11 +211,23 @@ def small_linear(x, w, bias, out, *, act_in: int = 0, alpha: float = 1.0, beta: 
     return out
 
 
-def timestep_sinusoid(t: torch.Tensor, out: torch.Tensor, round_bf16: bool = False):
-    _chk_f32(t, "t"); _chk_f32(out, "out")
+def timestep_freqs(dim: int, device, freq_shift: float = 0.0) -> torch.Tensor:
+    """fp32 [dim/2] frequency table, evaluated on the host with the reference's expression (embeddings.py:55-61)."""
+    import math
+    half = dim // 2
+    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32)
+    exponent = exponent / (half - freq_shift)
+    return torch.exp(exponent).to(device)
+
+
+def timestep_sinusoid(t: torch.Tensor, freqs: torch.Tensor, out: torch.Tensor, round_bf16: bool = False):
+    _chk_f32(t, "t"); _chk_f32(freqs, "freqs"); _chk_f32(out, "out")
     B, D = out.shape
+    if freqs.numel() != D // 2 or t.numel() != B:
+        raise RuntimeError("timestep_sinusoid: shape mismatch")
     lib = _lib.load()
-    _lib.check(lib.s2v_timestep_sinusoid(t.data_ptr(), out.data_ptr(), B, D, int(round_bf16), _stream()), "s2v_timestep_sinusoid")
+    _lib.check(lib.s2v_timestep_sinusoid(t.data_ptr(), freqs.data_ptr(), out.data_ptr(), B, D, int(round_bf16), _stream()),
+               "s2v_timestep_sinusoid")
     return out
 
 

@@ -127,10 +127,12 @@ S2V_API int s2v_small_linear(const float* x, int64_t ldx, const void* w, int64_t
                      int64_t ldo, int32_t B, int32_t N, int32_t K, int32_t act_in, float alpha, float beta,
                      int32_t round_bf16, void* stream);
 
-/* Sinusoidal timestep embedding, flip_sin_to_cos=True, freq_shift=0 (D/models/embeddings.py:27-78): out[b, 0:D/2] =
- * cos(t_b * f_i), out[b, D/2:] = sin(t_b * f_i), f_i = exp(-ln(10000) * i / (D/2)); rounded through bf16 when
- * round_bf16 (cogvideox_transformer_3d.py:490). */
-S2V_API int s2v_timestep_sinusoid(const float* t, float* out, int32_t B, int32_t D, int32_t round_bf16, void* stream);
+/* Sinusoidal timestep embedding, flip_sin_to_cos=True (D/models/embeddings.py:27-78): out[b, 0:D/2] = cos(t_b * f_i),
+ * out[b, D/2:] = sin(t_b * f_i); freqs[i] = exp(-ln(10000) * i / (D/2 - freq_shift)) is tabulated by the host in fp32
+ * with the reference's own expression so the argument is bit-identical; rounded through bf16 when round_bf16
+ * (cogvideox_transformer_3d.py:490). */
+S2V_API int s2v_timestep_sinusoid(const float* t, const float* freqs, float* out, int32_t B, int32_t D, int32_t round_bf16,
+                                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------ patchify / unpatchify
  * patchify: latents [NB, C, H, W] bf16 -> rows [NB*(H/p)*(W/p), C*p*p] bf16 (k = c*p*p + dy*p + dx), the im2col of

@@ -1,0 +1,337 @@
+"""GPU parity (run on the B200 box: pytest -m gpu).  Every test calls the product path (modules -> engine -> ctypes ->
+libs2v_b200.so) and compares with the CPU oracle on the same seeded inputs and with the committed reference goldens.
+
+Tolerances.  The product computes in bf16 with fp32 accumulation; the goldens are the reference's fp32 outputs.  The
+yardstick is the reference's OWN bf16 noise: the oracle executed in bf16 (same torch ops, bf16 tensors) differs from
+its fp32 run by e_ref; the product must satisfy  err <= max(2 * e_ref, floor).  Scheduler / index arithmetic is
+bit-exact (torch.equal)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import s2v_b200
+    assert s2v_b200._lib.load().s2v_device_check(0) == 0, "not a B200"
+    return torch.device("cuda:0")
+
+
+def _O():
+    from oracle import s2v_oracle as O
+    return O
+
+
+def load_flat_params(model, params):
+    """oracle-style flat dict ('<module>.weight', '<module>.lora_A.weight') -> product module tree (bf16 kept as given)."""
+    mods = dict(model.named_modules())
+    with torch.no_grad():
+        for k, v in params.items():
+            mod, _, leaf = k.rpartition(".")
+            base, _, ab = mod.rpartition(".")
+            if ab in ("lora_A", "lora_B"):
+                getattr(mods[base], ab)["default"].weight.copy_(v)
+            else:
+                layer = mods[mod]
+                layer = getattr(layer, "base_layer", layer)
+                getattr(layer, leaf).copy_(v)
+
+
+def rel_err(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12)), float((a - b).abs().max())
+
+
+def bf16_params(p):
+    return {k: v.to(BF16) for k, v in p.items()}
+
+
+def up(p):
+    return {k: v.float() for k, v in p.items()}
+
+
+def build_model(cfg, params, dev, lora):
+    import s2v_b200
+    m = s2v_b200.CogVideoXTransformer3DModel(
+        num_attention_heads=cfg.num_attention_heads, num_layers=cfg.num_layers, time_embed_dim=cfg.time_embed_dim,
+        text_embed_dim=cfg.text_embed_dim, use_rotary_positional_embeddings=cfg.use_rotary_positional_embeddings).to(BF16)
+    if lora:
+        s2v_b200.inject_lora(m, cfg.lora_rank, cfg.lora_alpha)
+    load_flat_params(m, params)
+    return m.to(dev)
+
+
+# ---------------------------------------------------------------------------------------------- block (configs[0])
+def _rope_small(O):
+    cos, sin = O.rope_3d_tables(64, ((0, 0), (8, 8)), (8, 8), 2)
+    return (cos[64:], sin[64:]), (cos[:64], sin[:64])
+
+
+@pytest.mark.parametrize("tag", ["lora_rope", "plain"])
+def test_block_tiny_vs_reference_golden(dev, golden_dir, tag):
+    import s2v_b200
+    O = _O()
+    fx = torch.load(os.path.join(golden_dir, "block_tiny.pt"))[tag]
+    cfg = O.TransformerConfig(**fx["cfg"])
+    p16 = bf16_params(O.synth_params(cfg, seed=fx["seed"]))
+    io = {k: v.to(BF16) for k, v in fx["io"].items()}
+    rv, rr = _rope_small(O) if cfg.use_rotary_positional_embeddings else (None, None)
+    # reference noise floor: oracle in bf16 vs golden fp32
+    ref16 = O.block_forward(p16, cfg, "transformer_blocks.0.", io["vid"], io["txt"], io["temb"], io["ref"], rv, rr)
+    blk = s2v_b200.CogVideoXBlock(dim=cfg.inner_dim, num_attention_heads=cfg.num_attention_heads, attention_head_dim=64,
+                                  time_embed_dim=cfg.time_embed_dim, attention_bias=True).to(BF16)
+    if cfg.lora_rank:
+        s2v_b200.inject_lora(blk, cfg.lora_rank, cfg.lora_alpha)
+    load_flat_params(blk, {k[len("transformer_blocks.0."):]: v for k, v in p16.items() if k.startswith("transformer_blocks.0.")})
+    blk = blk.to(dev)
+    got = blk(hidden_states=io["vid"].to(dev), encoder_hidden_states=io["txt"].to(dev), temb=io["temb"].to(dev),
+              enc_hidden_states1=io["ref"].to(dev), image_rotary_emb=rv, embed_ref_img=True, ref_img_seq_start=226,
+              ref_img_seq_end=290, position_delta=0, ref_image_rotary_emb=rr)
+    # oracle fp32 on the SAME bf16-rounded weights and inputs isolates kernel error from weight rounding
+    exact = O.block_forward(up(p16), cfg, "transformer_blocks.0.", io["vid"].float(), io["txt"].float(), io["temb"].float(),
+                            io["ref"].float(), rv, rr)
+    for g, r16, ex, key in zip(got, ref16, exact, ("vid", "txt", "ref")):
+        e_mine, _ = rel_err(g, ex)
+        e_ref, _ = rel_err(r16, ex)
+        e_gold, _ = rel_err(g, fx["out"][key])
+        print(f"block_tiny[{tag}].{key}: product {e_mine:.2e}  reference-bf16 {e_ref:.2e}  vs fp32 golden {e_gold:.2e}")
+        assert e_mine <= max(2.0 * e_ref, 4e-3), key
+        assert e_gold <= 3e-2, key
+
+
+@pytest.mark.parametrize("tag", ["2b_plain", "5b_lora_rope"])
+def test_block_cfg1_shape(dev, golden_dir, tag):
+    """BASELINE.json configs[0] at full width (D = 1920 / 3072), B = 2, text 226 + ref 64 + video 64 tokens."""
+    import s2v_b200
+    O = _O()
+    fx = torch.load(os.path.join(golden_dir, "block_cfg1.pt"))[tag]
+    cfg = O.TransformerConfig(**fx["cfg"])
+    p16 = bf16_params(O.synth_params(cfg, seed=21))
+    g = torch.Generator().manual_seed(22)
+    D = cfg.inner_dim
+    io = dict(vid=torch.randn(2, 64, D, generator=g), txt=torch.randn(2, 226, D, generator=g),
+              ref=torch.randn(2, 64, D, generator=g), temb=torch.randn(2, 512, generator=g))
+    io = {k: v.to(BF16) for k, v in io.items()}
+    rv, rr = _rope_small(O) if cfg.use_rotary_positional_embeddings else (None, None)
+    blk = s2v_b200.CogVideoXBlock(dim=D, num_attention_heads=cfg.num_attention_heads, attention_head_dim=64, time_embed_dim=512,
+                                  attention_bias=True).to(BF16)
+    if cfg.lora_rank:
+        s2v_b200.inject_lora(blk, cfg.lora_rank, cfg.lora_alpha)
+    load_flat_params(blk, {k[len("transformer_blocks.0."):]: v for k, v in p16.items() if k.startswith("transformer_blocks.0.")})
+    blk = blk.to(dev)
+    got = blk(io["vid"].to(dev), io["txt"].to(dev), io["temb"].to(dev), io["ref"].to(dev), image_rotary_emb=rv, embed_ref_img=True,
+              ref_img_seq_start=226, ref_img_seq_end=290, position_delta=0, ref_image_rotary_emb=rr)
+    ref16 = O.block_forward(p16, cfg, "transformer_blocks.0.", io["vid"], io["txt"], io["temb"], io["ref"], rv, rr)
+    for gt, r16, key in zip(got, ref16, ("vid", "txt", "ref")):
+        gold = fx["out"][key]
+        e_mine, _ = rel_err(gt[..., ::16], gold)
+        e_ref, _ = rel_err(r16[..., ::16], gold)
+        print(f"block_cfg1[{tag}].{key}: product {e_mine:.2e}  reference-bf16 {e_ref:.2e}")
+        assert e_mine <= max(2.0 * e_ref, 4e-3), key
+
+
+# ---------------------------------------------------------------------------------------------- whole transformer
+@pytest.mark.parametrize("tag", ["lora_rope", "plain_sincos"])
+def test_transformer_tiny_vs_reference_golden(dev, golden_dir, tag):
+    O = _O()
+    fx = torch.load(os.path.join(golden_dir, "transformer_tiny.pt"))[tag]
+    cfg = O.TransformerConfig(**fx["cfg"])
+    p16 = bf16_params(O.synth_params(cfg, seed=fx["seed"]))
+    io = fx["io"]
+    rv = rr = None
+    if cfg.use_rotary_positional_embeddings:
+        rv, rr = O.pipeline_rope_tables(io["hidden"].shape[3] * 8, io["hidden"].shape[4] * 8, io["hidden"].shape[1])
+    m = build_model(cfg, p16, dev, bool(cfg.lora_rank))
+    hid, ref, txt = io["hidden"].to(BF16), io["ref"].to(BF16), io["text"].to(BF16)
+    got = m(hidden_states=hid.to(dev), ref_img_states=ref.to(dev), encoder_hidden_states=txt.to(dev), timestep=io["timestep"].to(dev),
+            image_rotary_emb=rv, ref_image_rotary_emb=rr, return_dict=False, eval=True)[0]
+    assert got.shape == fx["out"].shape and got.dtype == BF16
+    exact = O.transformer_forward(up(p16), cfg, hid.float(), ref.float(), txt.float(), io["timestep"], rv, rr, eval=True)
+    ref16 = O.transformer_forward(p16, cfg, hid, ref, txt, io["timestep"], rv, rr, eval=True)
+    e_mine, _ = rel_err(got, exact)
+    e_ref, _ = rel_err(ref16, exact)
+    e_gold, _ = rel_err(got, fx["out"])
+    print(f"transformer_tiny[{tag}]: product {e_mine:.2e}  reference-bf16 {e_ref:.2e}  vs fp32 golden {e_gold:.2e}")
+    assert e_mine <= max(2.0 * e_ref, 5e-3)
+    assert e_gold <= 3e-2
+
+
+def test_merged_lora_matches_fused_lora(dev, golden_dir):
+    O = _O()
+    fx = torch.load(os.path.join(golden_dir, "transformer_tiny.pt"))["lora_rope"]
+    cfg = O.TransformerConfig(**fx["cfg"])
+    p16 = bf16_params(O.synth_params(cfg, seed=fx["seed"]))
+    io = fx["io"]
+    rv, rr = O.pipeline_rope_tables(io["hidden"].shape[3] * 8, io["hidden"].shape[4] * 8, io["hidden"].shape[1])
+    outs = []
+    for merge in (False, True):
+        m = build_model(cfg, p16, dev, True)
+        m.merge_lora = merge
+        outs.append(m(io["hidden"].to(dev, BF16), io["ref"].to(dev, BF16), io["text"].to(dev, BF16), io["timestep"].to(dev),
+                      image_rotary_emb=rv, ref_image_rotary_emb=rr, return_dict=False, eval=True)[0])
+    e, _ = rel_err(outs[1], outs[0])
+    assert e < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------- the loop
+@pytest.mark.parametrize("tag,dyn", [("fp32", False), ("fp32_dyncfg", True)])
+def test_pipeline_loop_vs_reference_golden(dev, golden_dir, tag, dyn):
+    """CustomCogVideoXPipeline.__call__ (3 DDIM steps, CFG 6, 480x720, 2 latent frames, LoRA, RoPE) against the
+    reference pipeline's fp32 output; yardstick = the reference pipeline's own bf16 run (fixture 'bf16')."""
+    import s2v_b200
+    O = _O()
+    fx = torch.load(os.path.join(golden_dir, "pipe_loop_tiny.pt"))
+    cfg = O.TransformerConfig(**fx["cfg"])
+    p16 = bf16_params(O.synth_params(cfg, seed=fx["seed"]))
+    m = build_model(cfg, p16, dev, True)
+    pipe = s2v_b200.CustomCogVideoXPipeline(None, None, m, None, s2v_b200.CogVideoXDDIMScheduler.for_cogvideox(1.0))
+    io = fx["io"]
+    out = pipe(prompt=None, ref_img_states=io["ref_img_states"], height=480, width=720, num_frames=5, num_inference_steps=3,
+               guidance_scale=6.0, use_dynamic_cfg=dyn, latents=io["latents"], prompt_embeds=io["prompt_embeds"],
+               negative_prompt_embeds=io["negative_prompt_embeds"], output_type="latent", return_dict=False, eval=True)[0]
+    gold = fx["runs"][tag]
+    e_mine, m_mine = rel_err(out, gold)
+    e_ref, m_ref = rel_err(fx["runs"]["bf16"], fx["runs"]["fp32"])
+    print(f"pipe_loop[{tag}]: product rel {e_mine:.2e} max {m_mine:.2e}; reference bf16-vs-fp32 rel {e_ref:.2e} max {m_ref:.2e}")
+    assert out.dtype == BF16 and out.shape == gold.shape
+    assert e_mine <= max(2.0 * e_ref, 1e-2)
+
+
+# ---------------------------------------------------------------------------------------------- scheduler: bit-exact
+def test_cfg_ddim_kernel_bit_exact_vs_cpu_reference_trace(dev, golden_dir):
+    """scalar_semantics='cpu': the fused kernel reproduces the reference scheduler's CPU trace bit for bit (guidance 1 with
+    uncond == cond makes CFG the identity: u + 1*(t-u) with t == u)."""
+    import s2v_b200
+    g = np.load(os.path.join(golden_dir, "scheduler_ddim.npz"))
+    for tag, snr in (("5b", 1.0), ("2b", 3.0)):
+        s = s2v_b200.CogVideoXDDIMScheduler.for_cogvideox(snr)
+        s.scalar_semantics = "cpu"
+        s.set_timesteps(50)
+        x = torch.from_numpy(g[f"trace_{tag}_sample0"]).to(BF16).to(dev)
+        for i, t in enumerate(s._timesteps_host):
+            v = torch.from_numpy(g[f"trace_{tag}_model_out"][i]).to(dev)
+            prev, x0 = s.step(v, t, x, return_dict=False)
+            assert prev.dtype == torch.float32
+            assert np.array_equal(prev.cpu().numpy(), g[f"trace_{tag}_prev"][i]), (tag, i)
+            assert np.array_equal(x0.cpu().numpy(), g[f"trace_{tag}_x0"][i]), (tag, i)
+            x = prev.to(BF16)
+
+
+def test_cfg_ddim_kernel_bit_exact_vs_torch_cuda(dev):
+    """scalar_semantics='cuda' (default): identical to the reference's expression evaluated by torch ON THE GPU with the
+    fp64 0-dim CPU coefficient tensors, including CFG with a non-trivial guidance and the final .to(bf16)."""
+    import s2v_b200
+    s = s2v_b200.CogVideoXDDIMScheduler.for_cogvideox(1.0)
+    s.set_timesteps(50)
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    lat = torch.randn(2, 13, 16, 60, 90, generator=gen).to(BF16).to(dev)
+    for t in (999, 979, 499, 19):
+        noise = torch.randn(4, 13, 16, 60, 90, generator=gen).to(BF16).to(dev)
+        got = s.step_cfg(noise, t, lat, 6.0)
+        npf = noise.float()
+        u, c = npf.chunk(2)
+        v = u + 6.0 * (c - u)
+        prev_t = t - 1000 // 50
+        a_t = s.alphas_cumprod[t]
+        a_prev = s.alphas_cumprod[prev_t] if prev_t >= 0 else s.final_alpha_cumprod
+        x0 = (a_t**0.5) * lat - ((1 - a_t) ** 0.5) * v
+        a_c = ((1 - a_prev) / (1 - a_t)) ** 0.5
+        b_c = a_prev**0.5 - a_t**0.5 * a_c
+        want = (a_c * lat + b_c * x0).to(BF16)
+        assert torch.equal(got, want), t
+
+
+# ---------------------------------------------------------------------------------------------- attention processor API
+def test_attention_processor_protocol(dev):
+    import s2v_b200
+    O = _O()
+    torch.manual_seed(3)
+    D, H = 128, 2
+    attn = s2v_b200.Attention(query_dim=D, dim_head=64, heads=H, bias=True).to(BF16)
+    with torch.no_grad():
+        for p_ in attn.parameters():
+            p_.copy_(torch.randn_like(p_.float()) * (0.05 if p_.dim() > 1 else 0.1) + (1.0 if p_.dim() == 1 and p_.numel() == 64 else 0))
+    attn = attn.to(dev)
+    enc = torch.randn(2, 226 + 64, D).to(BF16)
+    vid = torch.randn(2, 64, D).to(BF16)
+    rv, rr = _rope_small(O)
+    hv, he = attn(vid.to(dev), encoder_hidden_states=enc.to(dev), image_rotary_emb=rv, ref_img_seq_start=226, ref_img_seq_end=290,
+                  position_delta=0, embed_ref_img=True, ref_image_rotary_emb=rr, timestep=None, layer=0)
+    p = {f"a.{k}": v.detach().float().cpu() for k, v in attn.state_dict().items()}
+    cfg = O.TransformerConfig(num_attention_heads=H)
+    ev, ee = O.joint_attention(p, cfg, "a", vid.float(), enc.float(), 226, 64, rv, rr)
+    assert rel_err(hv, ev)[0] < 1.5e-2 and rel_err(he, ee)[0] < 1.5e-2
+    assert hv.shape == (2, 64, D) and he.shape == (2, 290, D)
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+def test_attention_full_size_properties(dev):
+    """cfg-3 sequence length (S = 19126, not a multiple of the 128-key tile): (1) V = const => output = const exactly up
+    to bf16 rounding (softmax rows sum to 1, masked tail keys contribute nothing); (2) linearity in V."""
+    from s2v_b200 import ops
+    torch.manual_seed(0)
+    B, S, H = 1, 19126, 4
+    qkv = torch.randn(B, S, 3 * H * 64, device=dev).to(BF16)
+    qkv.view(B, S, 3, H, 64)[:, :, 2] = 0.75
+    out = torch.empty(B, S, H * 64, device=dev, dtype=BF16)
+    ops.attention(qkv, out, H)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - 0.75).abs().max() < 0.75 * 2**-7
+    v1 = torch.randn(B, S, H, 64, device=dev).to(BF16)
+    v2 = torch.randn(B, S, H, 64, device=dev).to(BF16)
+    outs = []
+    for v in (v1, v2, (v1.float() + v2.float()).to(BF16)):
+        qkv.view(B, S, 3, H, 64)[:, :, 2] = v
+        o = torch.empty_like(out)
+        ops.attention(qkv, o, H)
+        outs.append(o.float())
+    assert (outs[2] - (outs[0] + outs[1])).abs().max() < 3e-3
+    # against torch SDPA in fp32 on a slice of query rows including the ragged tail
+    q, k, v = [t.transpose(1, 2).float() for t in qkv.view(B, S, 3, H, 64).unbind(2)]
+    ref = F.scaled_dot_product_attention(q[:, :, -300:], k, v)
+    assert rel_err(outs[2].view(B, S, H, 64).transpose(1, 2)[:, :, -300:], ref)[0] < 1e-2
+
+
+def test_linear_full_size_sampled_rows(dev):
+    """cfg-3 QKV projection shape with LoRA (M = 2*19126 rows, ragged last M tile): sampled rows vs fp32 matmul."""
+    from s2v_b200 import ops
+    torch.manual_seed(1)
+    M, K, N, r = 38252, 3072, 9216, 128
+    x = torch.randn(M, K, device=dev).to(BF16)
+    w = (0.02 * torch.randn(N, K, device=dev)).to(BF16)
+    b = (0.02 * torch.randn(N, device=dev)).to(BF16)
+    a = (0.02 * torch.randn(3 * r, K, device=dev)).to(BF16)
+    bb = (0.02 * torch.randn(N, r, device=dev)).to(BF16)
+    t = torch.empty(M, 3 * r, device=dev, dtype=BF16)
+    ops.linear(x, a, None, t, alpha=0.5)
+    out = torch.empty(M, N, device=dev, dtype=BF16)
+    ops.linear(x, w, b, out, lora_t=t, lora_b=bb, lora_group_n=N // 3)
+    idx = torch.cat([torch.randint(0, M, (96,), device=dev), torch.arange(M - 32, M, device=dev)])
+    xs = x[idx].float()
+    ts = (0.5 * xs @ a.float().t()).to(BF16).float()
+    ref = xs @ w.float().t() + b.float()
+    for g in range(3):
+        ref[:, g * 3072:(g + 1) * 3072] += ts[:, g * r:(g + 1) * r] @ bb[g * 3072:(g + 1) * 3072].float().t()
+    assert rel_err(out[idx], ref)[0] < 5e-3
+
+
+def test_c_abi_error_codes(dev):
+    import ctypes as C
+    from s2v_b200 import _lib
+    lib = _lib.load()
+    assert lib.s2v_attn_fwd(None, None, 1, 1, 1, 0.125, None) == -1
+    a = _lib.LinearArgs()
+    assert lib.s2v_linear(C.byref(a), None) == -1
+    assert b"null" in lib.s2v_last_error()
+    x = torch.zeros(8, 12, device=dev, dtype=BF16)  # K = 12 is not a multiple of 8
+    a.x, a.w, a.out, a.M, a.N, a.K, a.ldx, a.ldw, a.ldo = x.data_ptr(), x.data_ptr(), x.data_ptr(), 8, 8, 12, 12, 12, 8
+    assert lib.s2v_linear(C.byref(a), None) == -2

@@ -1,0 +1,191 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares, host logic
+(scheduler tables, RoPE / sincos tables, LoRA layout + packing, sharding plans) matches the reference goldens, and the
+product path FAILS LOUDLY without a B200 (no CPU / eager fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import s2v_b200
+from s2v_b200 import _lib, engine, lora, modules, ops, parallel, scheduler, tables
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ C ABI
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "s2v_b200.h")).read()
+    return sorted(set(re.findall(r"S2V_API\s+(?:const\s+char\*|int)\s+(s2v_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 19
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/s2v_b200.h but not exported"
+    # and the Python binding knows every compute entry point
+    for s in syms:
+        if s != "s2v_last_error":
+            assert s in _lib.SIGNATURES, s
+    assert lib.s2v_abi_version() == 1
+
+
+def test_linear_args_struct_matches_header_layout():
+    # field order and sizes of s2v_linear_args (LP64): 8-byte pointers / int64, 4-byte ints and float
+    import ctypes as C
+    assert C.sizeof(_lib.LinearArgs) == 8 * 9 + 4 * 2 + 8 * 2 + 4 * 4 + 4 + 4 + 8 + 4 * 5 + 4  # incl. tail padding
+    assert _lib.LinearArgs.mod.offset % 8 == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    assert lib.s2v_device_check(0) == -3  # S2V_E_NO_DEVICE
+    x = torch.zeros(8, 64, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.linear(x, x, None, torch.zeros(8, 8, dtype=torch.bfloat16))
+    m = modules.CogVideoXTransformer3DModel(num_attention_heads=1, num_layers=1, time_embed_dim=64, text_embed_dim=64).to(torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 1, 16, 4, 4), torch.zeros(1, 1, 16, 4, 4), torch.zeros(2, 4, 64), torch.tensor([1, 1]), eval=True)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "disentangled-subject-to-vid_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+\.*oracle", src, flags=re.M), f
+            assert "import_module(\"oracle" not in src and "s2v_oracle" not in src, f
+
+
+# ------------------------------------------------------------------ scheduler host arithmetic (bit-exact vs reference)
+@pytest.mark.parametrize("tag,snr", [("5b", 1.0), ("2b", 3.0)])
+def test_scheduler_tables_bit_exact(golden_dir, tag, snr):
+    g = np.load(os.path.join(golden_dir, "scheduler_ddim.npz"))
+    s = scheduler.CogVideoXDDIMScheduler.for_cogvideox(snr)
+    assert np.array_equal(s.alphas_cumprod.numpy(), g[f"alphas_cumprod_{tag}"])
+    for n in (50, 7, 30):
+        s.set_timesteps(n)
+        assert np.array_equal(s.timesteps.numpy(), g[f"timesteps_{tag}_{n}"])
+        assert s._timesteps_host == [int(t) for t in g[f"timesteps_{tag}_{n}"]]
+
+
+def test_scheduler_errors_match_reference():
+    s = scheduler.CogVideoXDDIMScheduler.for_cogvideox(1.0)
+    with pytest.raises(ValueError, match="set_timesteps"):
+        s.coefficients(999)
+    with pytest.raises(ValueError, match="cannot be larger"):
+        s.set_timesteps(1001)
+
+
+@pytest.mark.parametrize("tag,snr", [("5b", 1.0), ("2b", 3.0)])
+def test_scheduler_coefficients_reproduce_cpu_reference_trace(golden_dir, tag, snr):
+    """With scalar_semantics='cpu' the four fp32 coefficients + the kernel's rounding model (emulated here with torch
+    elementwise ops) reproduce the reference scheduler's 50-step trace bit for bit."""
+    g = np.load(os.path.join(golden_dir, "scheduler_ddim.npz"))
+    s = scheduler.CogVideoXDDIMScheduler.for_cogvideox(snr)
+    s.scalar_semantics = "cpu"
+    s.set_timesteps(50)
+    x = torch.from_numpy(g[f"trace_{tag}_sample0"]).to(torch.bfloat16)
+    rb = lambda z: z.to(torch.bfloat16).float()  # noqa: E731
+    for i, t in enumerate(s._timesteps_host):
+        sa, sb, a, b = (torch.tensor(c, dtype=torch.float32) for c in s.coefficients(t))
+        v = torch.from_numpy(g[f"trace_{tag}_model_out"][i])
+        x0 = rb(sa * x.float()) - sb * v
+        prev = rb(a * x.float()) + b * x0
+        assert np.array_equal(prev.numpy(), g[f"trace_{tag}_prev"][i]), i
+        x = prev.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------ tables
+def test_rope_tables_bit_exact(golden_dir):
+    import hashlib
+    g = np.load(os.path.join(golden_dir, "rope.npz"))
+    cos, sin = tables.rope_table_3d(64, ((0, 0), (8, 8)), (8, 8), 2)
+    assert np.array_equal(cos.numpy(), g["small_cos"]) and np.array_equal(sin.numpy(), g["small_sin"])
+    for tag, h, w, T in (("480x720_T14", 480, 720, 14), ("720x1280_T14", 720, 1280, 14), ("480x720_T3", 480, 720, 3)):
+        cos, sin = tables.joint_rope_table(h, w, T - 1)
+        assert hashlib.sha256(cos.numpy().tobytes()).hexdigest() == str(g[f"{tag}_cos_sha"])
+        assert hashlib.sha256(sin.numpy().tobytes()).hexdigest() == str(g[f"{tag}_sin_sha"])
+    for src in ((30, 45), (45, 80), (60, 60), (8, 12)):
+        (a, b), (c, d) = tables.crop_region_for_grid(src, 45, 30)
+        assert [a, b, c, d] == list(g[f"crop_{src[0]}x{src[1]}"])
+
+
+def test_sincos_table_matches_oracle():
+    from oracle import s2v_oracle as O
+    t = tables.sincos_table_3d(1920, 6, 4, 3, 1.875, 1.0)
+    ref = torch.from_numpy(O.sincos_pos_embed_3d(1920, 6, 4, 3, 1.875, 1.0)).flatten(0, 1).float()
+    assert torch.equal(t, ref)
+
+
+# ------------------------------------------------------------------ LoRA layout + packing
+def _tiny_model(**kw):
+    return modules.CogVideoXTransformer3DModel(num_attention_heads=2, num_layers=2, time_embed_dim=64, text_embed_dim=64, **kw)
+
+
+def test_state_dict_keys_match_reference_schema():
+    from oracle import s2v_oracle as O
+    m = _tiny_model(use_rotary_positional_embeddings=True)
+    cfg = O.TransformerConfig(num_attention_heads=2, num_layers=2, time_embed_dim=64, text_embed_dim=64)
+    want = O.param_shapes(cfg)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == {k: tuple(v) for k, v in want.items()}
+
+
+def test_lora_injection_targets_and_packing():
+    m = _tiny_model().to(torch.bfloat16)
+    names = lora.inject_lora(m, r=8, alpha=4.0)
+    per_block = {"attn1.to_q", "attn1.to_k", "attn1.to_v", "attn1.to_out.0", "norm1.linear", "norm2.linear", "ff.net.0.proj", "ff.net.2"}
+    want = {f"transformer_blocks.{i}.{s}" for i in range(2) for s in per_block} | {"patch_embed.proj", "patch_embed.text_proj"}
+    assert set(names) == want  # proj_out, norm_out.linear, time_embedding.* are NOT matched
+    sd = {f"transformer.{n}.lora_B.weight": torch.randn_like(m.get_submodule(n).lora_B["default"].weight) for n in names}
+    assert lora.load_lora_state_dict(m, sd) == len(names)
+    pb = engine.pack_block(m.transformer_blocks[0])
+    D = 128
+    assert pb.qkv.w.shape == (3 * D, D) and pb.qkv.a.shape == (24, D) and pb.qkv.bb.shape == (3 * D, 8) and pb.qkv.group_n == D
+    assert pb.qkv.scale == 0.5 and pb.ff1.bb.shape == (4 * D, 8) and pb.norm1.a.shape == (8, 64)
+    at = m.transformer_blocks[0].attn1
+    assert torch.equal(pb.qkv.w[D:2 * D], at.to_k.base_layer.weight) and torch.equal(pb.qkv.bb[2 * D:], at.to_v.lora_B["default"].weight)
+    # merged mode folds s*B*A into W with one rounding
+    pm = engine.pack_block(m.transformer_blocks[0], merge_lora=True)
+    w = at.to_q.base_layer.weight.float() + 0.5 * at.to_q.lora_B["default"].weight.float() @ at.to_q.lora_A["default"].weight.float()
+    assert pm.qkv.a is None and torch.equal(pm.qkv.w[:D], w.to(torch.bfloat16))
+
+
+def test_engine_rejects_non_bf16():
+    m = _tiny_model()
+    with pytest.raises(RuntimeError, match="bfloat16"):
+        engine.pack_block(m.transformer_blocks[0])
+
+
+# ------------------------------------------------------------------ pipeline input validation (reference error surface)
+def test_pipeline_errors_match_reference():
+    from s2v_b200 import CustomCogVideoXPipeline
+    m = _tiny_model().to(torch.bfloat16)
+    pipe = CustomCogVideoXPipeline(None, None, m, None, scheduler.CogVideoXDDIMScheduler.for_cogvideox())
+    with pytest.raises(ValueError, match="less than or equal to 49"):
+        pipe(prompt_embeds=torch.zeros(1, 4, 64), negative_prompt_embeds=torch.zeros(1, 4, 64), num_frames=53)
+    with pytest.raises(ValueError, match="divisible by 8"):
+        pipe(prompt_embeds=torch.zeros(1, 4, 64), negative_prompt_embeds=torch.zeros(1, 4, 64), height=481)
+    with pytest.raises(ValueError, match="Provide either"):
+        pipe()
+    with pytest.raises(ValueError, match="Cannot forward both"):
+        pipe(prompt="a", prompt_embeds=torch.zeros(1, 4, 64))
+
+
+# ------------------------------------------------------------------ sharding plans
+def test_shard_plans():
+    assert parallel.plan(8, 8, 3).prompts == [3] and parallel.plan(8, 8, 3).mode == "prompt"
+    assert parallel.plan(8, 4, 1).prompts == [1, 5]
+    p = parallel.plan(1, 2, 1)
+    assert p.mode == "cfg" and p.cfg_half == 1 and p.pair_ranks == [0, 1] and p.prompts == [0]
+    assert parallel.plan(2, 4, 2).prompts == [1] and parallel.plan(2, 4, 3).cfg_half == 1
+    with pytest.raises(ValueError):
+        parallel.plan(3, 2, 0)
+    pe = torch.arange(8).view(8, 1, 1).float()  # [neg0..3, pos0..3]
+    assert parallel.select_prompt_embeds(pe, 4, parallel.plan(4, 2, 1)).flatten().tolist() == [1, 3, 5, 7]
+    assert parallel.select_prompt_embeds(pe, 4, parallel.plan(4, 8, 5)).flatten().tolist() == [6]

@@ -212,7 +212,7 @@ def group_elementwise():
     # timestep sinusoid
     t = torch.tensor([999.0, 19.0], device=dev)
     o = torch.empty(2, 3072, device=dev)
-    ops.timestep_sinusoid(t, o)
+    ops.timestep_sinusoid(t, ops.timestep_freqs(3072, dev), o)
     half = 1536
     e = torch.exp(-math.log(10000) * torch.arange(half, device=dev, dtype=torch.float32) / half)
     arg = t[:, None] * e[None]
