@@ -1,23 +1,35 @@
 // Joint (text | reference image | video) self-attention forward for sm_100a, head_dim 64, no mask.
 //
-// One CTA owns one (batch, head) and TWO 128-row query tiles (256 query rows) and streams all S keys in 128-key tiles:
+// One CTA owns one (batch, head) and TWO 128-row query tiles (256 query rows) and streams all S keys in 64-key tiles.
 //
-//   warp 0        : TMA producer   — Q0,Q1 once, then K(j),V(j) tiles through a KV_STAGES-deep mbarrier ring
-//   warp 1        : tcgen05.mma issuer (single thread)
-//                     S_q(j)  = Q_q K(j)^T        SS-MMA  M128 N128 K64   -> TMEM columns [q*128, q*128+128)  (fp32)
-//                     O_q    += P_q(j) V(j)       TS-MMA  M128 N64  K128  -> TMEM columns [256+q*64, +64)     (fp32)
-//                   P_q(j) (bf16) aliases the first 64 columns of S_q; V is consumed straight from its [key][d] TMA
-//                   layout as an MN-major B operand, so no transpose is ever materialised.
+//   warp 0        : TMA producer   — K(t),V(t) tiles through a KV_STAGES-deep mbarrier ring (no Q in shared memory)
+//   warp 1        : tcgen05.mma issuer (single thread); BOTH operands A come from TMEM:
+//                     S_q(t)  = Q_q K(t)^T        TS-MMA  M128 N64 K64   -> TMEM S[q][t&1]  (fp32, double buffered)
+//                     O_q    += P_q(t) V(t)       TS-MMA  M128 N64 K64   -> TMEM O[q]       (fp32)
+//                   V is consumed straight from its [key][d] TMA layout as an MN-major B operand.
 //   warps 4..7    : softmax warpgroup for query tile 0   (one thread = one query row = one TMEM lane)
 //   warps 8..11   : softmax warpgroup for query tile 1
 //
-// The two query tiles ping-pong: while the tensor core runs PV_0(j) + S_0(j+1), warpgroup 1 does softmax on S_1(j),
-// and vice versa.  Softmax is the FA-style online form in the exp2 domain with LAZY rescaling: the running reference
-// max is only moved (and O, l rescaled in TMEM) when the row max grows by more than 2^8, so the O read-modify-write is
-// off the critical path for almost every tile.  exp2 arguments are formed with one FFMA (s*c - m*c).
+// Round-1 profile of the previous design (128-key tiles, P aliased onto S): XU pipe 70 %, tensor pipe 35 %, and the
+// softmax warps spent 36 % of their samples waiting for S(t+1), which could only be issued after P(t) had been
+// consumed.  Here S is double buffered and issued ONE TILE AHEAD of the PV product, so the softmax warps (the
+// MUFU-bound resource at head_dim 64: 16 ex2/clk/SM vs 8192 MMA flop/clk/SM) never wait for the tensor pipe:
 //
-// Global layout: qkv [B, S, 3*H*64] (q|k|v, heads contiguous) read through ONE 4-D tensor map
-// {64, 3H, S, B}; out [B, S, H*64].  Rows >= S are zero-filled by TMA; keys >= S are masked to -inf.
+//   tensor queue:   S0(t+1) S1(t+1) | PV0(t) PV1(t) | S0(t+2) S1(t+2) | PV0(t+1) ...
+//
+// Softmax (exp2 domain, FA-style online form) with three throughput measures, each taken from
+// tools/microbench_softmax.cu on B200 (profiles/r01_microbench.md):
+//   * no per-tile row max: the running reference m_ref only has to keep 2^(x - m_ref) inside fp32/bf16 range, so it
+//     is moved (and O, l rescaled in TMEM by the owning thread) only when a probability would exceed 2^64 — detected
+//     from the row-sum (inf/huge) and from the polynomial lanes' arguments; tile 0 takes the exact-max path;
+//   * packed fma.rn.f32x2 / add.rn.f32x2 (full rate on sm_100) for the exponent arguments and the row sums;
+//   * POLY of every 8 exponentials are evaluated on the FMA pipe (Cody-Waite split + degree-3 minimax, rel. error
+//     7.5e-5, far below the bf16 rounding of P) instead of MUFU.EX2.
+//
+// TMEM columns (512): Q0 0 | Q1 32 | P0 64 | P1 96 | S[0][0] 128 | S[0][1] 192 | S[1][0] 256 | S[1][1] 320 | O0 384 | O1 448
+//
+// Global layout: qkv [B, S, 3*H*64] (q|k|v, heads contiguous) read through ONE 4-D tensor map {64, 3H, S, B};
+// out [B, S, H*64].  Key rows >= S are zero-filled by TMA and masked to -inf; query rows >= S are not stored.
 #include "common.cuh"
 #include "host_util.h"
 #include "s2v_b200.h"
@@ -27,29 +39,77 @@ namespace s2v {
 constexpr int ATT_D = 64;
 constexpr int ATT_BQ = 128;         // rows per query tile (UMMA M)
 constexpr int ATT_QTILES = 2;       // query tiles per CTA
-constexpr int ATT_BK = 128;         // keys per tile
-constexpr int ATT_STAGES = 4;       // K/V ring depth
+constexpr int ATT_BK = 64;          // keys per tile
+constexpr int ATT_STAGES = 8;       // K/V ring depth
 constexpr int ATT_THREADS = 384;    // 12 warps
-constexpr uint32_t ATT_TILE_BYTES = ATT_BK * ATT_D * 2;  // 16 KB
-constexpr uint32_t ATT_SMEM_BYTES = (ATT_QTILES + 2 * ATT_STAGES) * ATT_TILE_BYTES + 1024 + 256;
-constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
+constexpr int ATT_POLY = 2;         // of every 8 exponentials, how many run on the FMA pipe
+constexpr uint32_t ATT_TILE_BYTES = ATT_BK * ATT_D * 2;  // 8 KB
+constexpr uint32_t ATT_SMEM_BYTES = 2 * ATT_STAGES * ATT_TILE_BYTES + 1024 + 256;
+constexpr float ATT_P_LIMIT_LOG2 = 64.0f;     // probabilities are kept below 2^64 relative to the reference max
+constexpr float ATT_SUM_LIMIT = 1.8446744e19f;  // 2^64
 
-constexpr uint32_t TM_S0 = 0, TM_O0 = 256;  // TMEM column map: S_q at q*128, O_q at 256 + q*64
+constexpr uint32_t TM_Q = 0, TM_P = 64, TM_S = 128, TM_O = 384;  // Q_q at q*32, P_q at 64+q*32, S[q][b] at 128+q*128+b*64, O_q at 384+q*64
+
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// 2^x for a packed pair (x <= 127): clamp below, round-to-nearest split x = n + f, degree-3 minimax of 2^f on
+// [-0.5, 0.5], exponent spliced in with an integer shift-add.  `xmax` tracks the largest argument seen (overflow guard).
+__device__ __forceinline__ void exp2_poly2(uint64_t X, float& r0, float& r1, float& xmax) {
+    const float MAGIC = 12582912.0f;  // 1.5 * 2^23: (x + MAGIC) holds round(x) in its low mantissa bits
+    float x0, x1;
+    unpack2(X, x0, x1);
+    xmax = fmax3(xmax, x0, x1);
+    x0 = fmaxf(x0, -125.0f);
+    x1 = fmaxf(x1, -125.0f);
+    X = pack2(x0, x1);
+    const uint64_t T = fadd2(X, pack2(MAGIC, MAGIC));
+    const uint64_t NF = fadd2(T, pack2(-MAGIC, -MAGIC));
+    const uint64_t F = ffma2(NF, pack2(-1.0f, -1.0f), X);
+    uint64_t P = ffma2(pack2(0.05517166f, 0.05517166f), F, pack2(0.24261112f, 0.24261112f));
+    P = ffma2(P, F, pack2(0.69326099f, 0.69326099f));
+    P = ffma2(P, F, pack2(0.99992807f, 0.99992807f));
+    float p0, p1, t0, t1;
+    unpack2(P, p0, p1);
+    unpack2(T, t0, t1);
+    r0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+    r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int S, int H, float scale_log2) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H,
+                float scale_log2) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                     // 2 x 16 KB
-    uint8_t* sK = smem + ATT_QTILES * ATT_TILE_BYTES;       // STAGES x 16 KB
-    uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;         // STAGES x 16 KB
+    uint8_t* sK = smem;                                     // STAGES x 8 KB
+    uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;         // STAGES x 8 KB
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_STAGES * ATT_TILE_BYTES);
-    uint64_t* q_full = bars;                  // 1
-    uint64_t* kv_full = bars + 1;             // STAGES
-    uint64_t* kv_empty = kv_full + ATT_STAGES;  // STAGES
-    uint64_t* s_full = kv_empty + ATT_STAGES;   // 2
-    uint64_t* p_ready = s_full + 2;           // 2
-    uint64_t* o_final = p_ready + 2;          // 1
+    uint64_t* kv_full = bars;                     // STAGES
+    uint64_t* kv_empty = kv_full + ATT_STAGES;    // STAGES
+    uint64_t* s_full = kv_empty + ATT_STAGES;     // 4: [q][buf]
+    uint64_t* p_ready = s_full + 4;               // 2
+    uint64_t* p_free = p_ready + 2;               // 2
+    uint64_t* q_ready = p_free + 2;               // 1
+    uint64_t* o_final = q_ready + 1;              // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
 
     const int warp = threadIdx.x >> 5;
@@ -60,15 +120,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ ou
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
-        mbar_init(q_full, 1);
         for (int s = 0; s < ATT_STAGES; ++s) {
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], 1);
         }
+        for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
         for (int q = 0; q < 2; ++q) {
-            mbar_init(&s_full[q], 1);
             mbar_init(&p_ready[q], 4);  // one arrive per softmax warp
+            mbar_init(&p_free[q], 1);
         }
+        mbar_init(q_ready, 8);
         mbar_init(o_final, 1);
         fence_barrier_init();
     }
@@ -83,16 +144,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ ou
         if (warp == 0) {
             // ---------------------------------------------------------------- TMA producer
             if (lane == 0) {
-                mbar_arrive_expect_tx(q_full, ATT_QTILES * ATT_TILE_BYTES);
-                for (int q = 0; q < ATT_QTILES; ++q)
-                    tma_load_4d(&tmQKV, q_full, sQ + q * ATT_TILE_BYTES, 0, head, q_row0 + q * ATT_BQ, batch);
                 int stage = 0;
                 uint32_t phase = 0;
-                for (int j = 0; j < n_kv; ++j) {
+                for (int t = 0; t < n_kv; ++t) {
                     mbar_wait(&kv_empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
-                    tma_load_4d(&tmQKV, &kv_full[stage], sK + stage * ATT_TILE_BYTES, 0, H + head, j * ATT_BK, batch);
-                    tma_load_4d(&tmQKV, &kv_full[stage], sV + stage * ATT_TILE_BYTES, 0, 2 * H + head, j * ATT_BK, batch);
+                    tma_load_4d(&tmQKV, &kv_full[stage], sK + stage * ATT_TILE_BYTES, 0, H + head, t * ATT_BK, batch);
+                    tma_load_4d(&tmQKV, &kv_full[stage], sV + stage * ATT_TILE_BYTES, 0, 2 * H + head, t * ATT_BK, batch);
                     if (++stage == ATT_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -101,74 +159,69 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ ou
             }
         } else if (warp == 1) {
             // ---------------------------------------------------------------- MMA issuer
-            constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BK, 0, 0);   // S = Q K^T   (both K-major)
+            constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BK, 0, 0);   // S = Q K^T   (A in TMEM, B K-major)
             constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_D, 0, 1);    // O += P V    (A in TMEM, B MN-major)
-            auto issue_s = [&](int q, int stage) {
-                const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ + q * ATT_TILE_BYTES), 16, 1024);
+            auto issue_s = [&](int q, int stage, int buf) {
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + stage * ATT_TILE_BYTES), 16, 1024);
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)
-                    umma_ss(tmem_base + TM_S0 + q * 128, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc_s, k != 0);
+                    umma_ts(tmem_base + TM_S + q * 128 + buf * 64, tmem_base + TM_Q + q * 32 + k * 8, bdesc + uint64_t(k * 2),
+                            idesc_s, k != 0);
             };
             auto issue_pv = [&](int q, int stage, bool accumulate) {
-                // V tile [128 keys][64 d]: 16 keys per MMA = two 8-row groups = 2048 bytes
+                // V tile [64 keys][64 d]: 16 keys per MMA = two 8-row groups = 2048 bytes
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + stage * ATT_TILE_BYTES), 1024, 1024);
 #pragma unroll
                 for (int k = 0; k < ATT_BK / 16; ++k)
-                    umma_ts(tmem_base + TM_O0 + q * 64, tmem_base + TM_S0 + q * 128 + k * 8, bdesc + uint64_t(k * 128),
-                            idesc_o, (accumulate || k != 0) ? 1u : 0u);
+                    umma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_P + q * 32 + k * 8, bdesc + uint64_t(k * 128), idesc_o,
+                            (accumulate || k != 0) ? 1u : 0u);
             };
-            mbar_wait(q_full, 0);
-            mbar_wait(&kv_full[0], 0);
-            tc_fence_after();
-            if (lane == 0) {
-                issue_s(0, 0);
+            // The whole issue loop runs in ONE elected thread: with `elect.sync` the compiler knows a single lane is
+            // active and feeds tcgen05.mma's uniform-register operands directly; under `if (lane == 0)` it wrapped every
+            // MMA in a warp-uniformisation loop (~80 issue cycles per MMA, which made the issuer the bottleneck).
+            if (elect_one()) {
+                mbar_wait(q_ready, 0);
+                mbar_wait(&kv_full[0], 0);
+                tc_fence_after();
+                issue_s(0, 0, 0);
                 umma_commit(&s_full[0]);
-                issue_s(1, 0);
-                umma_commit(&s_full[1]);
+                issue_s(1, 0, 0);
+                umma_commit(&s_full[2]);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int t = 0; t < n_kv; ++t) {
+                    int nstage = stage + 1;
+                    uint32_t nphase = phase;
+                    if (nstage == ATT_STAGES) {
+                        nstage = 0;
+                        nphase ^= 1;
+                    }
+                    // ---- scores of tile t+1 for both query tiles (their TMEM buffers were drained before p_ready(t-1))
+                    if (t + 1 < n_kv) {
+                        mbar_wait(&kv_full[nstage], nphase);
+                        tc_fence_after();
+                        const int nb = (t + 1) & 1;
+                        issue_s(0, nstage, nb);
+                        umma_commit(&s_full[nb]);
+                        issue_s(1, nstage, nb);
+                        umma_commit(&s_full[2 + nb]);
+                    }
+                    // ---- O_q += P_q(t) V(t)
+                    mbar_wait(&p_ready[0], t & 1);
+                    tc_fence_after();
+                    issue_pv(0, stage, t != 0);
+                    umma_commit(&p_free[0]);
+                    mbar_wait(&p_ready[1], t & 1);
+                    tc_fence_after();
+                    issue_pv(1, stage, t != 0);
+                    umma_commit(&p_free[1]);
+                    umma_commit(&kv_empty[stage]);  // every MMA reading K(t)/V(t) has been issued before this point
+                    if (t + 1 == n_kv) umma_commit(o_final);
+                    stage = nstage;
+                    phase = nphase;
+                }
             }
             __syncwarp();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_kv; ++j) {
-                int nstage = stage + 1;
-                uint32_t nphase = phase;
-                if (nstage == ATT_STAGES) {
-                    nstage = 0;
-                    nphase ^= 1;
-                }
-                const bool has_next = (j + 1 < n_kv);
-                // ---- query tile 0
-                mbar_wait(&p_ready[0], j & 1);
-                tc_fence_after();
-                if (lane == 0) issue_pv(0, stage, j != 0);
-                __syncwarp();
-                if (has_next) {
-                    mbar_wait(&kv_full[nstage], nphase);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        issue_s(0, nstage);
-                        umma_commit(&s_full[0]);
-                    }
-                    __syncwarp();
-                }
-                // ---- query tile 1
-                mbar_wait(&p_ready[1], j & 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    issue_pv(1, stage, j != 0);
-                    umma_commit(&kv_empty[stage]);  // every MMA reading K(j)/V(j) has been issued before this point
-                    if (has_next) {
-                        issue_s(1, nstage);
-                        umma_commit(&s_full[1]);
-                    } else {
-                        umma_commit(o_final);
-                    }
-                }
-                __syncwarp();
-                stage = nstage;
-                phase = nphase;
-            }
         }
     } else {
         // -------------------------------------------------------------------- softmax warpgroups
@@ -176,85 +229,132 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ ou
         const int q = (warp - 4) >> 2;          // query tile of this warpgroup
         const int lq = warp & 3;                // TMEM lane quarter
         const uint32_t lane_off = uint32_t(lq * 32) << 16;
-        const uint32_t tS = tmem_base + lane_off + TM_S0 + q * 128;
-        const uint32_t tO = tmem_base + lane_off + TM_O0 + q * 64;
+        const uint32_t tSb = tmem_base + lane_off + TM_S + q * 128;
+        const uint32_t tP = tmem_base + lane_off + TM_P + q * 32;
+        const uint32_t tO = tmem_base + lane_off + TM_O + q * 64;
         const int row = q_row0 + q * ATT_BQ + lq * 32 + lane;
 
-        float m_ref = -INFINITY;   // reference max (raw score units) used in the exponent
-        float l_sum = 0.f;
+        // ---- this thread's query row -> TMEM (A operand of S = Q K^T: lane = row, 32-bit column c = elements 2c, 2c+1)
+        {
+            uint32_t qr[32];
+            if (row < S) {
+                const uint4* src = reinterpret_cast<const uint4*>(qkv + ((long long)batch * S + row) * (long long)(3 * H * ATT_D) +
+                                                                  head * ATT_D);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 v = __ldg(src + i);
+                    qr[4 * i] = v.x; qr[4 * i + 1] = v.y; qr[4 * i + 2] = v.z; qr[4 * i + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) qr[i] = 0u;
+            }
+            tmem_st32(tmem_base + lane_off + TM_Q + q * 32, qr);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_ready);
+        }
 
-        for (int j = 0; j < n_kv; ++j) {
-            mbar_wait(&s_full[q], j & 1);
+        float m_ref = -INFINITY;   // reference max (raw score units) used in the exponent
+        float mneg = 0.f;          // -m_ref * scale_log2
+        float l_sum = 0.f;
+        const uint64_t C2 = pack2(scale_log2, scale_log2);
+
+        for (int t = 0; t < n_kv; ++t) {
+            const int buf = t & 1;
+            mbar_wait(&s_full[q * 2 + buf], (t >> 1) & 1);
             tc_fence_after();
-            uint32_t s[128];
+            uint32_t s[64];
             {
                 uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
                 uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-                uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
-                uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
-                tmem_ld32(tS, s0);
-                tmem_ld32(tS + 32, s1);
-                tmem_ld32(tS + 64, s2);
-                tmem_ld32(tS + 96, s3);
+                tmem_ld32(tSb + buf * 64, s0);
+                tmem_ld32(tSb + buf * 64 + 32, s1);
                 tmem_ld_wait();
             }
-            const int valid = S - j * ATT_BK;  // keys valid in this tile (>= 128 except for the last tile)
+            const int valid = S - t * ATT_BK;  // keys valid in this tile (>= 64 except for the last tile)
             if (valid < ATT_BK) {
 #pragma unroll
-                for (int i = 0; i < 128; ++i)
+                for (int i = 0; i < 64; ++i)
                     if (i >= valid) s[i] = __float_as_uint(-INFINITY);
             }
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            uint32_t pk[32];
+            float tsum;
+            bool redo = (t == 0);
+            if (!redo) {
+                // ---- fast path: exponentials against the standing reference max
+                const uint64_t M2 = pack2(mneg, mneg);
+                uint64_t acc0 = 0ull, acc1 = 0ull;
+                float xmax = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 128; i += 4) {
-                mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-                mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-                mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-                mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+                for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const uint64_t X = ffma2(pack2(__uint_as_float(s[i + 2 * h]), __uint_as_float(s[i + 2 * h + 1])), C2, M2);
+                        float p0, p1;
+                        if (2 * h < ATT_POLY) {
+                            exp2_poly2(X, p0, p1, xmax);
+                        } else {
+                            float x0, x1;
+                            unpack2(X, x0, x1);
+                            p0 = ex2_approx(x0);
+                            p1 = ex2_approx(x1);
+                        }
+                        if (h & 1) acc1 = fadd2(acc1, pack2(p0, p1)); else acc0 = fadd2(acc0, pack2(p0, p1));
+                        pk[i / 2 + h] = pack_bf16x2(p0, p1);
+                    }
+                }
+                float a, b, c, d;
+                unpack2(acc0, a, b);
+                unpack2(acc1, c, d);
+                tsum = (a + b) + (c + d);
+                const bool bad = !(tsum < ATT_SUM_LIMIT) || (xmax > ATT_P_LIMIT_LOG2);
+                redo = __any_sync(0xffffffffu, bad);
             }
-            const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-            if (j == 0) {
-                m_ref = m_tile;
-            } else {
-                const bool need = (m_tile - m_ref) * scale_log2 > ATT_RESCALE_THRESHOLD;
-                if (__any_sync(0xffffffffu, need)) {
-                    // s_full[q] of tile j was committed after PV_q(j-1): O_q is quiescent here.
-                    const float factor = need ? ex2_approx((m_ref - m_tile) * scale_log2) : 1.0f;
-                    if (need) m_ref = m_tile;
+            if (t != 0) {
+                mbar_wait(&p_free[q], (t - 1) & 1);   // PV_q(t-1) has consumed P_q(t-1) and left O_q quiescent
+                tc_fence_after();
+            }
+            if (redo) {
+                // ---- exact-max path (tile 0, or a probability would leave the 2^64 window): move the reference
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 64; i += 4) {
+                    mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+                    mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+                }
+                const float m_new = fmaxf(m_ref, fmaxf(mx0, mx1));
+                if (t != 0) {
+                    const float factor = ex2_approx((m_ref - m_new) * scale_log2);   // 1 when the reference does not move
                     l_sum *= factor;
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
+                    for (int cb = 0; cb < 2; ++cb) {
                         uint32_t o[32];
-                        tmem_ld32(tO + c * 32, o);
+                        tmem_ld32(tO + cb * 32, o);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-                        tmem_st32(tO + c * 32, o);
+                        tmem_st32(tO + cb * 32, o);
                     }
                     tmem_st_wait();
                 }
-            }
-            const float mneg = -m_ref * scale_log2;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            uint32_t pk[64];
+                m_ref = m_new;
+                mneg = -m_new * scale_log2;
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 128; i += 4) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, mneg));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg));
-                const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), scale_log2, mneg));
-                const float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), scale_log2, mneg));
-                a0 += p0; a1 += p1; a2 += p2; a3 += p3;
-                pk[i / 2] = pack_bf16x2(p0, p1);
-                pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+                for (int i = 0; i < 64; i += 2) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, mneg));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg));
+                    a0 += p0;
+                    a1 += p1;
+                    pk[i / 2] = pack_bf16x2(p0, p1);
+                }
+                tsum = a0 + a1;
             }
-            l_sum += (a0 + a1) + (a2 + a3);
-            {
-                const uint32_t(&p0)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]);
-                const uint32_t(&p1)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]);
-                tmem_st32(tS, p0);
-                tmem_st32(tS + 32, p1);
-                tmem_st_wait();
-            }
+            l_sum += tsum;
+            tmem_st32(tP, pk);
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[q]);
@@ -316,6 +416,7 @@ extern "C" int s2v_attn_fwd(const void* qkv, void* o, int32_t B, int32_t S, int3
     }
     dim3 grid((S + ATT_BQ * ATT_QTILES - 1) / (ATT_BQ * ATT_QTILES), H, B);
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm, static_cast<bf16*>(o), S, H, scale_log2);
+    attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm, static_cast<const bf16*>(qkv), static_cast<bf16*>(o), S, H,
+                                                                   scale_log2);
     return check_launch("attn_fwd_kernel");
 }

@@ -130,20 +130,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
+        // single elected thread for the whole loop (see attn_tcgen05.cu: `if (lane == 0)` around each tcgen05.mma makes the
+        // compiler wrap it in a warp-uniformisation loop)
         constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < kb_total; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
                     const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
@@ -154,14 +156,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     umma_commit(&empty_bar[stage]);
                     if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);
-                }
-                __syncwarp();
-                if (++stage == Cfg::STAGES) {
-                    stage = 0;
-                    phase ^= 1;
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int q = warp & 3;  // TMEM lane quarter this warp may touch

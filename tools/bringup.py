@@ -134,6 +134,21 @@ def group_attn():
         q, k, v = [t.view(B, S, H, 64).transpose(1, 2).float() for t in qkv.chunk(3, dim=-1)]
         ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
         ok &= report(f"attn B{B} S{S} H{H} x{scale_in}", out, ref, 2e-2)
+    # reference-max moves: late keys whose scores exceed the first tile's by > 2^64 (exact-max path + O/l rescale in TMEM),
+    # ragged sizes around the 64-key tile and the 256-row CTA
+    for (B, S, H, boost_at) in [(1, 1, 1, None), (1, 63, 1, None), (1, 65, 2, None), (1, 257, 1, None), (1, 700, 2, 300),
+                                (2, 1500, 2, 1111), (1, 1500, 1, 64)]:
+        qkv = torch.randn(B, S, 3 * H * 64, device=dev)
+        if boost_at is not None:
+            qkv[:, boost_at:boost_at + 3, H * 64:2 * H * 64] *= 40.0     # a few keys with huge |k|: scores up to ~ +-2000
+            qkv[:, boost_at + 100:boost_at + 101, H * 64:2 * H * 64] *= 90.0
+        qkv = qkv.to(torch.bfloat16)
+        out = torch.full((B, S, H * 64), float("nan"), device=dev, dtype=torch.bfloat16)
+        ops.attention(qkv, out, H)
+        torch.cuda.synchronize()
+        q, k, v = [t.view(B, S, H, 64).transpose(1, 2).float() for t in qkv.chunk(3, dim=-1)]
+        ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
+        ok &= report(f"attn_edge B{B} S{S} H{H} boost@{boost_at}", out, ref, 2e-2)
     B, S, H = 2, 19126, 48
     qkv = torch.randn(B, S, 3 * H * 64, device=dev).to(torch.bfloat16)
     out = torch.empty(B, S, H * 64, device=dev, dtype=torch.bfloat16)
