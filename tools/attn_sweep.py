@@ -1,0 +1,43 @@
+"""Sweep the attention kernel's polynomial-exp2 fraction at the cfg-3 shape, interleaved with torch SDPA as a clock reference."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+
+from s2v_b200 import _lib, ops
+
+B, S, H = 2, 19126, 48
+torch.manual_seed(0)
+qkv = torch.randn(B, S, 3 * H * 64, device="cuda").to(torch.bfloat16)
+out = torch.empty(B, S, H * 64, device="cuda", dtype=torch.bfloat16)
+q, k, v = [t.view(B, S, H, 64).transpose(1, 2) for t in qkv.chunk(3, dim=-1)]
+fl = 4.0 * B * H * S * S * 64
+
+
+def timed(fn, iters=5):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+lib = _lib.load()
+vals = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4]
+res = {p: [] for p in vals}
+ref = []
+for rep in range(3):
+    ref.append(timed(lambda: F.scaled_dot_product_attention(q, k, v)))
+    for p in vals:
+        lib.s2v_attn_set_poly16(p)
+        res[p].append(timed(lambda: ops.attention(qkv, out, H)))
+print(json.dumps({"torch_sdpa_ms": [round(x, 3) for x in ref], "tflops": round(fl / min(ref) / 1e9, 1)}))
+for p in vals:
+    print(json.dumps({"poly16": p, "ms": [round(x, 3) for x in res[p]], "best_tflops": round(fl / min(res[p]) / 1e9, 1)}))
