@@ -75,6 +75,21 @@ class CogVideoXDDIMScheduler:
                    clip_sample=False, num_train_timesteps=1000, prediction_type="v_prediction", rescale_betas_zero_snr=True,
                    set_alpha_to_one=True, timestep_spacing="trailing")
 
+    @classmethod
+    def from_reference(cls, scheduler):
+        """Build from an already constructed reference `CogVideoXDDIMScheduler` (duck-typed: reads its `.config`), keeping
+        any `set_timesteps` state — the one-line swap shown in INTEGRATION.md."""
+        cfg = scheduler.config
+        get = (lambda k, d=None: cfg[k] if k in cfg else d) if isinstance(cfg, dict) else (lambda k, d=None: getattr(cfg, k, d))
+        keys = ("num_train_timesteps", "beta_start", "beta_end", "beta_schedule", "trained_betas", "clip_sample", "set_alpha_to_one",
+                "steps_offset", "prediction_type", "clip_sample_range", "sample_max_value", "timestep_spacing",
+                "rescale_betas_zero_snr", "snr_shift_scale")
+        new = cls(**{k: get(k) for k in keys if get(k, None) is not None or k == "trained_betas"})
+        n = getattr(scheduler, "num_inference_steps", None)
+        if n is not None:
+            new.set_timesteps(n, device=getattr(getattr(scheduler, "timesteps", None), "device", None))
+        return new
+
     # ------------------------------------------------------------------ reference surface
     def scale_model_input(self, sample: torch.Tensor, timestep=None) -> torch.Tensor:
         return sample
