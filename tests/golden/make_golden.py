@@ -240,11 +240,48 @@ def gen_pipe_loop():
     torch.save(fix, os.path.join(HERE, "pipe_loop_tiny.pt"))
 
 
+# ------------------------------------------------------------------ G. VAE decoder (row V)
+def gen_vae():
+    """The reference AutoencoderKLCogVideoX (decoder half) with seeded weights: one decoder call with a conv-cache chain,
+    the untiled `_decode`, and the tiled + blended `decode` (tiling and slicing enabled as in S/inference.py:206-207)."""
+    from diffusers.models.autoencoders.autoencoder_kl_cogvideox import AutoencoderKLCogVideoX
+
+    from oracle import vae_oracle as V
+
+    cfg = V.VaeConfig(block_out_channels=(64, 128, 128, 128), layers_per_block=1, sample_height=64, sample_width=96,
+                      scaling_factor=0.7)
+    params = V.synth_decoder_params(cfg, seed=51)
+    vae = AutoencoderKLCogVideoX(block_out_channels=cfg.block_out_channels, layers_per_block=cfg.layers_per_block,
+                                 latent_channels=16, sample_height=cfg.sample_height, sample_width=cfg.sample_width,
+                                 scaling_factor=cfg.scaling_factor, temporal_compression_ratio=4).float().eval()
+    missing, unexpected = vae.load_state_dict(params, strict=False)
+    assert not unexpected and all(k.startswith("encoder.") for k in missing), (unexpected, [k for k in missing if not k.startswith("encoder.")][:5])
+    assert set(params) == {k for k in vae.state_dict() if k.startswith("decoder.")}
+    g = torch.Generator().manual_seed(52)
+    z = torch.randn(1, 16, 5, 8, 12, generator=g)            # 5 latent frames (batches [0:3] [3:5]), 8x12 latent = 64x96 px
+    fix = dict(cfg=cfg.__dict__, seed=51, z=z, weight_checksum=float(sum(v.double().sum() for v in params.values())))
+    with torch.no_grad():
+        # one tile-sized decoder call chain with caches (4x6 latent tile)
+        zt = z[:, :, :, :4, :6]
+        y0, cache = vae.decoder(zt[:, :, :3], conv_cache=None)
+        y1, _ = vae.decoder(zt[:, :, 3:5], conv_cache=cache)
+        fix["decoder_chain"] = dict(y0=y0, y1=y1)
+        fix["decode_untiled"] = vae.decode(z).sample                     # tiling off
+        vae.enable_slicing()
+        vae.enable_tiling()
+        fix["decode_tiled"] = vae.decode(z).sample                       # 3x3 tiles, blended
+        z2 = torch.cat([z, 0.5 * z.flip(3)], dim=0)
+        fix["decode_tiled_b2_sum"] = float(vae.decode(z2).sample.double().sum())
+    print("vae", {k: tuple(v.shape) for k, v in fix.items() if isinstance(v, torch.Tensor)}, fix["decode_tiled"].abs().mean())
+    torch.save(fix, os.path.join(HERE, "vae_tiny.pt"))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["sched", "rope", "block", "transformer", "pipe"]
+    which = sys.argv[1:] or ["sched", "rope", "block", "transformer", "pipe", "vae"]
     if "sched" in which: gen_scheduler()
     if "rope" in which: gen_rope()
     if "block" in which: gen_block()
     if "transformer" in which: gen_transformer()
     if "pipe" in which: gen_pipe_loop()
+    if "vae" in which: gen_vae()
