@@ -9,9 +9,10 @@ importlib.import_module("disentangled-subject-to-vid_b200").
     engine                       weight packing, workspaces, the fused block / model forward
     modules, pipeline, scheduler the reference's operator surface (same names, arguments, errors)
     lora                         PEFT-layout LoRA adapters, read in place
+    vae                          3D causal VAE decoder (implicit-GEMM convs) behind AutoencoderKLCogVideoX.decode
     parallel                     prompt / CFG sharding over the GPUs of one node (torch.distributed)
 """
-from . import _lib, engine, lora, modules, ops, parallel, pipeline, scheduler, tables  # noqa: F401
+from . import _lib, engine, lora, modules, ops, parallel, pipeline, scheduler, tables, vae  # noqa: F401
 from .lora import inject_lora, load_lora_state_dict  # noqa: F401
 from .modules import (  # noqa: F401
     Attention,
@@ -22,5 +23,6 @@ from .modules import (  # noqa: F401
 )
 from .pipeline import CogVideoXPipelineOutput, CustomCogVideoXPipeline  # noqa: F401
 from .scheduler import CogVideoXDDIMScheduler  # noqa: F401
+from .vae import AutoencoderKLCogVideoX, attach_vae  # noqa: F401
 
 __version__ = "0.1.0"

@@ -32,6 +32,20 @@ class LinearArgs(C.Structure):
     ]
 
 
+class ConvArgs(C.Structure):
+    """s2v_conv_args (include/s2v_b200.h)."""
+
+    _fields_ = [
+        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("w", C.c_void_p), ("ldw", C.c_int64),
+        ("bias", C.c_void_p),
+        ("res", C.c_void_p), ("ldres", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("T", C.c_int32), ("t_pad", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
+        ("taps", C.c_int32),
+    ]
+
+
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 # name -> argtypes; every function returns int except s2v_last_error
@@ -55,6 +69,14 @@ SIGNATURES = {
     "s2v_add_rows": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "s2v_cfg_ddim_step": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp],
     "s2v_ddim_step": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp],
+    "s2v_conv_gemm": [C.POINTER(ConvArgs), _vp],
+    "s2v_vae_latent_rows": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
+    "s2v_vae_latent_im2col": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
+    "s2v_vae_groupnorm_stats": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
+    "s2v_vae_spatialnorm_silu": [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "s2v_vae_upsample_nearest": [_vp, _vp, C.POINTER(C.c_int32), _i32, _i32, _i32, _i32, _vp],
+    "s2v_vae_volume_to_video": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "s2v_vae_blend": [_vp, _vp, _i64, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _vp],
 }
 
 _lib = None

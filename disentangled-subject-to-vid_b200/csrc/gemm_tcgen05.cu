@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include "s2v_b200.h"
+#include <string.h>
 
 namespace s2v {
 
@@ -28,7 +29,15 @@ struct GemmKParams {
     float alpha;
     const float* mod;
     int mod_stride, gate_off_text, gate_off_other, rows_per_batch, text_len;
+    // implicit-GEMM convolution (S2V_EPI_CONV): K block kb reads channels [(kb % cin_blocks)*64, +64) of A rows shifted by
+    // tap_off[kb / cin_blocks]; output row m is stored at row out_row0 + m, zeroed when it is a spatial border position
+    int taps, cin_blocks, a_row0, out_row0, Hp, Wp;
+    int tap_off[27];
+    const bf16* res;
+    long long ldres;
 };
+
+constexpr int S2V_EPI_CONV = 3;
 
 template <int BN>
 struct GemmCfg {
@@ -71,7 +80,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
     const int num_n = (p.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
-    const int kb1 = (p.K + GEMM_BK - 1) / GEMM_BK;
+    const int kb1 = (EPI == S2V_EPI_CONV) ? p.taps * p.cin_blocks : (p.K + GEMM_BK - 1) / GEMM_BK;
     const int kb2 = (p.K2 + GEMM_BK - 1) / GEMM_BK;
     const int kb_total = kb1 + kb2;
 
@@ -114,7 +123,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     if (kb < kb1) {
-                        tma_load_2d(&tmA, &full_bar[stage], sa, kb * GEMM_BK, m0);
+                        if (EPI == S2V_EPI_CONV) {
+                            const int tap = kb / p.cin_blocks;
+                            tma_load_2d(&tmA, &full_bar[stage], sa, (kb - tap * p.cin_blocks) * GEMM_BK,
+                                        p.a_row0 + m0 + p.tap_off[tap]);
+                        } else {
+                            tma_load_2d(&tmA, &full_bar[stage], sa, kb * GEMM_BK, m0);
+                        }
                         tma_load_2d(&tmB, &full_bar[stage], sb, kb * GEMM_BK, n0);
                     } else {
                         const int kk = (kb - kb1) * GEMM_BK;
@@ -178,7 +193,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = m_blk * GEMM_BM + q * 32 + lane;
             const bool row_ok = row < p.M;
             const int n0 = n_blk * BN;
-            bf16* orow = p.out + (long long)row * p.ldo + n0;
+            bf16* orow = p.out + (long long)(row + (EPI == S2V_EPI_CONV ? p.out_row0 : 0)) * p.ldo + n0;
+            bool border = false;
+            const bf16* rrow = nullptr;
+            if (EPI == S2V_EPI_CONV && row_ok) {
+                const int rem = row % (p.Hp * p.Wp);
+                const int hp = rem / p.Wp, wp = rem - hp * p.Wp;
+                border = (hp == 0) | (hp == p.Hp - 1) | (wp == 0) | (wp == p.Wp - 1);
+                if (p.res) rrow = p.res + (long long)(row + p.out_row0) * p.ldres + n0;
+            }
             const float* gate = nullptr;
             if (EPI == S2V_EPI_GATE_RESIDUAL && row_ok) {
                 const int b = row / p.rows_per_batch;
@@ -224,6 +247,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     f[2 * j + 1] = bf16_hi(rw[j]) + gg[2 * j + 1] * f[2 * j + 1];
                                 }
                             }
+                            if (EPI == S2V_EPI_CONV) {
+                                if (rrow) {
+                                    const uint4 rr = *reinterpret_cast<const uint4*>(rrow + c * 32 + g8 * 8);
+                                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        f[2 * j] += bf16_lo(rw[j]);
+                                        f[2 * j + 1] += bf16_hi(rw[j]);
+                                    }
+                                }
+                                if (border) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+                                }
+                            }
                             uint4 o;
                             o.x = pack_bf16x2(f[0], f[1]);
                             o.y = pack_bf16x2(f[2], f[3]);
@@ -249,12 +287,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------------ host side
+struct ConvExtra {
+    int taps, cin, a_row0, out_row0, Hp, Wp;
+    int64_t a_rows;          // rows of the A volume (TMA bound)
+    const int* tap_off;
+    const void* res;
+    long long ldres;
+};
+
 template <int BN, int EPI>
-static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream) {
+static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const ConvExtra* conv = nullptr) {
     using Cfg = GemmCfg<BN>;
     CUtensorMap tmA, tmB, tmA2, tmB2;
     int rc;
-    if ((rc = make_tmap_2d_bf16(&tmA, a->x, a->K, a->M, a->ldx, GEMM_BK, GEMM_BM))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tmA, a->x, conv ? conv->cin : a->K, conv ? conv->a_rows : a->M, a->ldx, GEMM_BK, GEMM_BM))) return rc;
     if ((rc = make_tmap_2d_bf16(&tmB, a->w, a->K, a->N, a->ldw, GEMM_BK, BN))) return rc;
     const int K2 = a->lora_t ? a->lora_r : 0;
     if (K2) {
@@ -275,6 +321,13 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream) {
     p.mod = a->mod;
     p.mod_stride = a->mod_stride; p.gate_off_text = a->gate_off_text; p.gate_off_other = a->gate_off_other;
     p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->M; p.text_len = a->text_len;
+    p.taps = 1; p.cin_blocks = (a->K + GEMM_BK - 1) / GEMM_BK; p.a_row0 = 0; p.out_row0 = 0; p.Hp = 1; p.Wp = 1;
+    p.res = nullptr; p.ldres = 0;
+    if (conv) {
+        p.taps = conv->taps; p.cin_blocks = (conv->cin + GEMM_BK - 1) / GEMM_BK; p.a_row0 = conv->a_row0; p.out_row0 = conv->out_row0;
+        p.Hp = conv->Hp; p.Wp = conv->Wp; p.res = static_cast<const bf16*>(conv->res); p.ldres = conv->ldres;
+        for (int i = 0; i < 27; ++i) p.tap_off[i] = i < conv->taps ? conv->tap_off[i] : 0;
+    }
 
     auto kern = gemm_tcgen05_kernel<BN, EPI>;
     static bool attr_done = false;
@@ -336,4 +389,40 @@ extern "C" int s2v_ffn_up_gelu_lora(const s2v_linear_args* a, void* stream) {
 extern "C" int s2v_ffn_down_lora_gate_residual(const s2v_linear_args* a, void* stream) {
     if (a && a->epilogue != S2V_EPI_GATE_RESIDUAL) return set_error(S2V_E_BADARG, "ffn_down: epilogue must be GATE_RESIDUAL");
     return s2v_linear(a, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ implicit-GEMM convolution
+extern "C" int s2v_conv_gemm(const s2v_conv_args* c, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!c || !c->x || !c->w || !c->out) return set_error(S2V_E_BADARG, "s2v_conv_gemm: null pointer");
+    if (c->taps != 1 && c->taps != 9 && c->taps != 27) return set_error(S2V_E_BADARG, "s2v_conv_gemm: taps must be 1, 9 or 27");
+    if (c->T <= 0 || c->Hp < 3 || c->Wp < 3 || c->cin <= 0 || c->cout <= 0) return set_error(S2V_E_BADARG, "s2v_conv_gemm: empty problem");
+    if ((c->cin % 8) || (c->cout % 8) || (c->ldx % 8) || (c->ldo % 8) || (c->ldw % 8) || (c->res && (c->ldres % 8)))
+        return set_error(S2V_E_UNSUPPORTED, "s2v_conv_gemm: channel counts and leading dims must be multiples of 8");
+    if (c->taps > 1 && (c->cin % 64)) return set_error(S2V_E_UNSUPPORTED, "s2v_conv_gemm: 3x3(x3) taps need Cin % 64 == 0");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const long long plane = (long long)c->Hp * c->Wp;
+    const long long M = (long long)c->T * plane;
+    if (M > 0x7fffffffLL || (long long)(c->T + c->t_pad) * plane > 0x7fffffffLL)
+        return set_error(S2V_E_UNSUPPORTED, "s2v_conv_gemm: more than 2^31 rows");
+    int off[27];
+    if (c->taps == 27) {
+        for (int dt = 0; dt < 3; ++dt)
+            for (int dh = 0; dh < 3; ++dh)
+                for (int dw = 0; dw < 3; ++dw) off[(dt * 3 + dh) * 3 + dw] = (int)((dt - 2) * plane + (dh - 1) * c->Wp + (dw - 1));
+    } else if (c->taps == 9) {
+        for (int dh = 0; dh < 3; ++dh)
+            for (int dw = 0; dw < 3; ++dw) off[dh * 3 + dw] = (dh - 1) * c->Wp + (dw - 1);
+    } else {
+        off[0] = 0;
+    }
+    s2v_linear_args a;
+    memset(&a, 0, sizeof(a));
+    a.x = c->x; a.ldx = c->ldx; a.w = c->w; a.ldw = c->ldw; a.bias = c->bias; a.out = c->out; a.ldo = c->ldo;
+    a.M = (int)M; a.N = c->cout; a.K = c->taps * c->cin; a.epilogue = S2V_EPI_CONV; a.alpha = 1.0f;
+    ConvExtra ex;
+    ex.taps = c->taps; ex.cin = c->cin; ex.a_row0 = (int)(c->t_pad * plane); ex.out_row0 = (int)(c->t_pad * plane);
+    ex.Hp = c->Hp; ex.Wp = c->Wp; ex.a_rows = (long long)(c->T + c->t_pad) * plane; ex.tap_off = off; ex.res = c->res; ex.ldres = c->ldres;
+    return (c->cout >= 256) ? launch_gemm<256, S2V_EPI_CONV>(&a, stream, &ex) : launch_gemm<128, S2V_EPI_CONV>(&a, stream, &ex);
 }

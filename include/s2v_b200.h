@@ -163,6 +163,70 @@ S2V_API int s2v_cfg_ddim_step(const void* noise_pred, const void* latents, void*
 S2V_API int s2v_ddim_step(const float* model_output, const void* sample, float* prev_out, float* x0_out, int64_t n,
                           float sqrt_alpha, float sqrt_beta, float a_coef, float b_coef, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ VAE decoder (row V)
+ * Activations of the 3D causal VAE decoder live in padded channels-last VOLUMES  [t_pad + T, Hp, Wp, C]  bf16 with
+ * Hp = H + 2, Wp = W + 2 (one zero pixel all round) and t_pad = 2 leading frames that hold the temporal context of a
+ * causal convolution (the reference's conv_cache, or copies of the first frame).  Row index r = (t*Hp + hp)*Wp + wp.
+ *
+ * s2v_conv_gemm: implicit-GEMM convolution on tcgen05 — no im2col is materialised; each of the `taps` kernel taps is a
+ * block of K columns whose A rows are the SAME volume shifted by a constant row offset (TMA coordinates), so a
+ * 3x3x3 causal conv (taps 27), a per-frame 3x3 conv (taps 9) and a 1x1x1 conv (taps 1) are one kernel:
+ *   out[t_pad*Hp*Wp + m, :] = bias + res[...] + sum_tap x[t_pad*Hp*Wp + m + off(tap), :] * w[:, tap*cin : (tap+1)*cin]^T
+ * for m in [0, T*Hp*Wp); border positions (hp or wp on the zero ring) are stored as 0 so the result is again a valid
+ * padded volume.  w is [cout, taps*cin] with tap = (dt*3 + dh)*3 + dw (torch weight .permute(0,2,3,4,1)).
+ * Replaces CogVideoXCausalConv3d / CogVideoXSafeConv3d (autoencoder_kl_cogvideox.py:43-66,129-137), the Conv2d of
+ * CogVideoXUpsample3D (upsampling.py:407-410) and the residual add of CogVideoXResnetBlock3D (:318). */
+typedef struct {
+    const void* x;   int64_t ldx;    /* input volume, [t_pad + T, Hp, Wp, cin] bf16 */
+    const void* w;   int64_t ldw;    /* [cout, taps*cin] bf16 */
+    const void* bias;                /* [cout] bf16 or NULL */
+    const void* res; int64_t ldres;  /* optional residual volume (same geometry as out) or NULL */
+    void* out;       int64_t ldo;    /* output volume, [t_pad + T, Hp, Wp, cout] bf16 */
+    int32_t T, t_pad, Hp, Wp, cin, cout, taps;
+} s2v_conv_args;
+S2V_API int s2v_conv_gemm(const s2v_conv_args* c, void* stream);
+
+/* Latent tile -> GEMM operands.  z is ONE sample [C, Tz, hz, wz] bf16; the tile is frames [f0, f0+T), rows [i0, i0+ht),
+ * cols [j0, j0+wt); values are multiplied by `scale` (= 1/scaling_factor, pipeline_cogvideox.py:348) in fp32 and rounded.
+ * latent_rows: channels-last rows [T*ht*wt, ldr] (columns >= C zero) — the A operand of the fused conv_y|conv_b 1x1x1 GEMM
+ * of every CogVideoXSpatialNorm3D (autoencoder_kl_cogvideox.py:183-184).
+ * latent_im2col: [T*(ht+2)*(wt+2), 27*C] — conv_in's A operand over the padded output grid; frame index max(f0+t+dt-2, 0)
+ * reproduces CogVideoXCausalConv3d's cache / first-frame replication (:120-127). */
+S2V_API int s2v_vae_latent_rows(const void* z, void* rows, int32_t C, int32_t Tz, int32_t hz, int32_t wz, int32_t f0, int32_t T,
+                                int32_t i0, int32_t j0, int32_t ht, int32_t wt, int32_t ldr, float scale, void* stream);
+S2V_API int s2v_vae_latent_im2col(const void* z, void* col, int32_t C, int32_t Tz, int32_t hz, int32_t wz, int32_t f0, int32_t T,
+                                  int32_t i0, int32_t j0, int32_t ht, int32_t wt, float scale, void* stream);
+
+/* GroupNorm(G groups, eps) statistics of the T real frames (interior positions) of a volume: stats[g] = (mean, rstd) fp32.
+ * `partial` is caller-owned scratch of max_blocks*C*2 floats; the two-stage reduction has a fixed order (deterministic).
+ * nn.GroupNorm inside CogVideoXSpatialNorm3D (autoencoder_kl_cogvideox.py:163,186). */
+S2V_API int s2v_vae_groupnorm_stats(const void* x, float* partial, float* stats, int32_t T, int32_t H, int32_t W, int32_t C, int32_t G,
+                                    int32_t max_blocks, float eps, void* stream);
+
+/* out = SiLU( GroupNorm(x) * conv_y(zq') + conv_b(zq') ) written as a padded volume (border ring zero).  yb is the fused
+ * conv_y|conv_b output at LATENT resolution [Tl*hl*wl, 2C]; frame_src[t] (host array, T <= 32) is the latent frame that
+ * nearest-neighbour interpolation assigns to output frame t (first frame kept separate when T is odd and > 1,
+ * autoencoder_kl_cogvideox.py:173-181); H/hl and W/wl must be powers of two.
+ * Replaces CogVideoXSpatialNorm3D.forward + the SiLU that follows it (:167-188, :297, :306, :974). */
+S2V_API int s2v_vae_spatialnorm_silu(const void* x, void* out, const float* stats, const void* gamma, const void* beta, const void* yb,
+                                     const int32_t* frame_src, int32_t T, int32_t H, int32_t W, int32_t C, int32_t G, int32_t hl,
+                                     int32_t wl, void* stream);
+
+/* Nearest 2x upsampling in H and W with the temporal index map frame_src[t] (host array, T_out <= 32), written as the padded
+ * input volume of the per-frame 3x3 conv.  The interpolate half of CogVideoXUpsample3D.forward (upsampling.py:385-405). */
+S2V_API int s2v_vae_upsample_nearest(const void* x, void* out, const int32_t* frame_src, int32_t T_out, int32_t H_in, int32_t W_in,
+                                     int32_t C, void* stream);
+
+/* video[c, f0 + t, h, w] = vol[2 + t, h + 1, w + 1, c] for c < Cout: conv_out's volume (ldc channels) -> [Cout, Tv, H, W] bf16. */
+S2V_API int s2v_vae_volume_to_video(const void* vol, void* video, int32_t T, int32_t H, int32_t W, int32_t ldc, int32_t Cout, int32_t Tv,
+                                    int32_t f0, void* stream);
+
+/* In-place seam ramp of tiled_decode (blend_v / blend_h, autoencoder_kl_cogvideox.py:1284-1298) on bf16 tensors with
+ * arbitrary element strides (outer, blended axis, other axis): b[o,y,x] = a[o, a_len-extent+y, x]*(1-y/extent) + b[o,y,x]*(y/extent),
+ * with torch's bf16 rounding points. */
+S2V_API int s2v_vae_blend(const void* a, void* b, int64_t n_outer, int32_t extent, int32_t n_other, int32_t a_len, int64_t a_so,
+                          int64_t a_sy, int64_t a_sx, int64_t b_so, int64_t b_sy, int64_t b_sx, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ stage wrappers
  * Thin named entry points (the per-stage ABI proposed in SURVEY.md §8b); each forwards to s2v_linear. */
 S2V_API int s2v_qkv_lora(const s2v_linear_args* a, void* stream);                     /* K1: to_q|to_k|to_v + LoRA, bias      */

@@ -1,0 +1,133 @@
+"""Row V on the GPU: the sm_100a VAE decoder against the reference-generated golden (fp32) and against the reference
+arithmetic run in bf16 (the oracle on CPU with bf16 weights/inputs = the noise floor two bf16 pipelines differ by)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vae_oracle as V  # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a B200")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def fix(golden_dir):
+    return torch.load(os.path.join(golden_dir, "vae_tiny.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def vae(dev, fix):
+    import s2v_b200
+    cfg = V.VaeConfig(**fix["cfg"])
+    p = V.synth_decoder_params(cfg, seed=fix["seed"])
+    m = s2v_b200.AutoencoderKLCogVideoX(block_out_channels=cfg.block_out_channels, layers_per_block=cfg.layers_per_block,
+                                        sample_height=cfg.sample_height, sample_width=cfg.sample_width, scaling_factor=cfg.scaling_factor)
+    missing, unexpected = m.load_state_dict(p, strict=True)
+    return m.to(torch.bfloat16).to(dev), cfg, p
+
+
+def rel(a, b):
+    return float((a.float().cpu() - b.float()).norm() / b.float().norm())
+
+
+def bf16_floor(cfg, p, z, tiling):
+    """The same arithmetic in bf16 on the CPU (weights, inputs and every intermediate rounded like the reference's bf16 run)."""
+    pb = {k: v.to(torch.bfloat16) for k, v in p.items()}
+    with torch.no_grad():
+        return V.decode(pb, cfg, z.to(torch.bfloat16), use_tiling=tiling).float()
+
+
+def test_conv_gemm_matches_torch_conv3d(dev):
+    """The implicit-GEMM causal 3x3x3 convolution alone, incl. the temporal context frames and the zeroed border ring."""
+    import ctypes as C
+    from s2v_b200 import _lib
+    from s2v_b200._lib import ConvArgs
+    torch.manual_seed(0)
+    T, H, W, cin, cout = 3, 10, 13, 64, 128
+    x = torch.randn(1, cin, T + 2, H, W)                       # frames 0,1 = temporal context
+    w = torch.randn(cout, cin, 3, 3, 3) / (27 * cin) ** 0.5
+    b = 0.1 * torch.randn(cout)
+    xb, wb, bb = x.to(torch.bfloat16), w.to(torch.bfloat16), b.to(torch.bfloat16)
+    want = F.conv3d(F.pad(xb.float(), (1, 1, 1, 1)), wb.float(), bb.float())            # [1, cout, T, H, W]
+    vol = torch.zeros(T + 2, H + 2, W + 2, cin, dtype=torch.bfloat16)
+    vol[:, 1:-1, 1:-1] = xb[0].permute(1, 2, 3, 0)
+    vol = vol.to(dev)
+    res = torch.randn(T + 2, H + 2, W + 2, cout).to(torch.bfloat16).to(dev)
+    out = torch.full((T + 2, H + 2, W + 2, cout), float("nan"), dtype=torch.bfloat16, device=dev)
+    w2 = wb.permute(0, 2, 3, 4, 1).reshape(cout, 27 * cin).contiguous().to(dev)
+    a = ConvArgs()
+    a.x, a.ldx, a.w, a.ldw, a.bias = vol.data_ptr(), cin, w2.data_ptr(), 27 * cin, bb.to(dev).data_ptr()
+    bias_dev = bb.to(dev)
+    a.bias = bias_dev.data_ptr()
+    a.res, a.ldres, a.out, a.ldo = res.data_ptr(), cout, out.data_ptr(), cout
+    a.T, a.t_pad, a.Hp, a.Wp, a.cin, a.cout, a.taps = T, 2, H + 2, W + 2, cin, cout, 27
+    _lib.check(_lib.load().s2v_conv_gemm(C.byref(a), torch.cuda.current_stream().cuda_stream), "s2v_conv_gemm")
+    torch.cuda.synchronize()
+    got = out[2:].float().cpu()
+    assert torch.all(got[:, 0] == 0) and torch.all(got[:, -1] == 0) and torch.all(got[:, :, 0] == 0) and torch.all(got[:, :, -1] == 0)
+    want_cl = want[0].permute(1, 2, 3, 0) + res[2:, 1:-1, 1:-1].float().cpu()
+    err = float((got[:, 1:-1, 1:-1] - want_cl).abs().max() / want_cl.abs().max())
+    assert err < 1e-2, err          # one bf16 rounding of the output
+
+
+def test_blend_bit_exact_vs_torch_cuda(dev, vae):
+    m, _, _ = vae
+    torch.manual_seed(1)
+    a = torch.randn(1, 3, 5, 24, 40, device=dev).to(torch.bfloat16)
+    for axis, fn, ext in ((3, m.blend_v, 7), (4, m.blend_h, 9)):
+        # neighbours share the size of the non-blended axis (same tile row / column), the blended axis may differ
+        b = torch.randn(1, 3, 5, 20 if axis == 3 else 24, 40 if axis == 3 else 33, device=dev).to(torch.bfloat16)
+        want = b.clone()
+        for y in range(ext):   # the reference expression on CUDA bf16 tensors (autoencoder_kl_cogvideox.py:1284-1298)
+            if axis == 3:
+                want[:, :, :, y, :] = a[:, :, :, -ext + y, :] * (1 - y / ext) + want[:, :, :, y, :] * (y / ext)
+            else:
+                want[:, :, :, :, y] = a[:, :, :, :, -ext + y] * (1 - y / ext) + want[:, :, :, :, y] * (y / ext)
+        got = fn(a, b.clone(), ext)
+        assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("tiling", [False, True])
+def test_decode_vs_reference_golden(dev, fix, vae, tiling):
+    m, cfg, p = vae
+    z = fix["z"]
+    if tiling:
+        m.enable_slicing()
+        m.enable_tiling()
+    else:
+        m.disable_tiling()
+    with torch.no_grad():
+        got = m.decode(z.to(torch.bfloat16).to(dev)).sample
+    torch.cuda.synchronize()
+    want = fix["decode_tiled" if tiling else "decode_untiled"]
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    floor = rel(bf16_floor(cfg, p, z, tiling), want)
+    err = rel(got, want)
+    print(f"vae decode[tiling={tiling}]: product {err:.3e}  reference-arithmetic-in-bf16 {floor:.3e}  (vs fp32 reference golden)")
+    assert err < max(1.5 * floor, 5e-3), (err, floor)
+
+
+def test_decode_batch_and_chain(dev, fix, vae):
+    m, cfg, p = vae
+    m.enable_slicing()
+    m.enable_tiling()
+    z2 = torch.cat([fix["z"], 0.5 * fix["z"].flip(3)], dim=0)
+    with torch.no_grad():
+        out = m.decode(z2.to(torch.bfloat16).to(dev)).sample
+    assert out.shape[0] == 2
+    s = float(out.double().sum())
+    assert abs(s - fix["decode_tiled_b2_sum"]) < 2e-2 * float(out.double().abs().sum())
+    # one tile-sized call chain with conv caches (the decoder.forward surface)
+    m.disable_tiling()
+    with torch.no_grad():
+        y = m.decode(fix["z"][:, :, :, :4, :6].to(torch.bfloat16).to(dev)).sample
+    want = torch.cat([fix["decoder_chain"]["y0"], fix["decoder_chain"]["y1"]], dim=2)
+    assert rel(y, want) < 1.5e-2
