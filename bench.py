@@ -263,11 +263,49 @@ def run_product(args, w):
         "model_tflops": round(total_fl * world * args.steps / (ms / 1e3) / 1e12 / world, 1),
         "build_s": round(t_build, 1),
     }
+    if args.vae and w["model"] != "tiny":
+        line["vae_decode"] = vae_leg(dev, lat_d, w)
     if args.cpu_baseline:
         line["cpu_baseline"] = cpu_sample(w, steps=1, warmup=0)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def vae_leg(dev, latents, w):
+    """Row V next to the loop (outside the timed region): decode this rank's final latents with the 3D causal VAE
+    (random-init CogVideoX decoder, the reference's default tiled schedule) and report seconds per video."""
+    import torch
+
+    import s2v_b200
+    with torch.device("meta"):
+        vae = s2v_b200.AutoencoderKLCogVideoX(scaling_factor=0.7)
+    vae = vae.to_empty(device=dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    with torch.no_grad():
+        for n, p in vae.named_parameters():
+            if "norm_layer.weight" in n:
+                p.copy_(1 + 0.1 * torch.randn(p.shape, device=dev, generator=g))
+            elif n.endswith("bias"):
+                p.copy_(0.05 * torch.randn(p.shape, device=dev, generator=g))
+            else:
+                p.copy_(torch.randn(p.shape, device=dev, generator=g) / p[0].numel() ** 0.5)
+    vae = vae.to(torch.bfloat16)
+    vae.enable_slicing()
+    vae.enable_tiling()
+    pipe = s2v_b200.CustomCogVideoXPipeline(None, None, None, vae, None)
+    times = []
+    for _ in range(2):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        video = pipe.decode_latents(latents[:1])
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) / 1e3)
+    assert torch.isfinite(video.float()).all()
+    return {"seconds_per_video": round(min(times), 3), "schedule": "tiled 3x3 x 6 temporal batches (reference default), bf16",
+            "output": list(video.shape), "conv_tflops": round(7.09e14 / min(times) / 1e12, 1)}
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm (oracle port)
@@ -331,6 +369,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-vae", dest="vae", action="store_false", help="skip the VAE-decode leg (reported outside the timed loop)")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false", help="skip the host-buffer loop (profiler runs; not a valid bench line)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -340,5 +379,6 @@ if __name__ == "__main__":
         run_reference(args, w)
     else:
         if args.gpus > 1:
-            args.cpu_baseline = args.cpu_baseline and False
+            args.cpu_baseline = False
+            args.vae = False
         run_product(args, w)

@@ -19,6 +19,7 @@ There is no CPU / eager fallback: the modules only hold parameters.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import types
 from typing import Dict, List, Optional, Tuple
 
@@ -101,7 +102,7 @@ class CogVideoXDecoder3D(nn.Module):
         ch = list(reversed(block_out_channels))
         self.conv_in = CogVideoXCausalConv3d(in_channels, ch[0], 3)
         self.mid_block = _Block(ch[0], ch[0], 2, in_channels, norm_num_groups, None)
-        t_levels = int(round(torch.log2(torch.tensor(float(temporal_compression_ratio))).item()))
+        t_levels = int(round(math.log2(float(temporal_compression_ratio))))
         blocks, prev = [], ch[0]
         for i, c in enumerate(ch):
             last = i == len(ch) - 1
@@ -169,7 +170,7 @@ class VaeDecoderEngine:
         self.layers = int(layers_per_block)
         self.G = int(norm_num_groups)
         self.zc = int(latent_channels)
-        self.t_levels = int(round(torch.log2(torch.tensor(float(temporal_compression_ratio))).item()))
+        self.t_levels = int(round(math.log2(float(temporal_compression_ratio))))
         p = {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix)}
         if not p:
             raise RuntimeError("no decoder.* parameters found")
