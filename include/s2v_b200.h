@@ -92,6 +92,8 @@ S2V_API int s2v_attn_fwd(const void* qkv, void* o, int32_t B, int32_t S, int32_t
 /* Tuning knob (process-wide, not thread-safe): how many of every 8 exponential PAIRS the softmax evaluates with the FMA-pipe
  * polynomial instead of MUFU.EX2 (0..8).  Every setting computes the same function to within 7.5e-5 relative error. */
 S2V_API int s2v_attn_set_poly16(int32_t pairs_of_8);
+/* Tuning knob: delay (ns) before the second query tile's softmax warpgroup starts, to keep the two warpgroups out of phase. */
+S2V_API int s2v_attn_set_skew_ns(int32_t ns);
 
 /* ------------------------------------------------------------------------------------------------ AdaLN-Zero
  * out[b,s,:] = LayerNorm_D(x[b,s,:]; w, bias, eps) * (1 + scale) + shift, where (shift, scale) come from the

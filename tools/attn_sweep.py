@@ -30,14 +30,16 @@ def timed(fn, iters=5):
 
 
 lib = _lib.load()
-vals = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4]
+# usage: attn_sweep.py poly16[:skew_ns] ...
+vals = [tuple(int(x) for x in (a + ":0").split(":")[:2]) for a in sys.argv[1:]] or [(p, 0) for p in (0, 1, 2, 3, 4)]
 res = {p: [] for p in vals}
 ref = []
 for rep in range(3):
     ref.append(timed(lambda: F.scaled_dot_product_attention(q, k, v)))
     for p in vals:
-        lib.s2v_attn_set_poly16(p)
+        lib.s2v_attn_set_poly16(p[0])
+        lib.s2v_attn_set_skew_ns(p[1])
         res[p].append(timed(lambda: ops.attention(qkv, out, H)))
 print(json.dumps({"torch_sdpa_ms": [round(x, 3) for x in ref], "tflops": round(fl / min(ref) / 1e9, 1)}))
 for p in vals:
-    print(json.dumps({"poly16": p, "ms": [round(x, 3) for x in res[p]], "best_tflops": round(fl / min(res[p]) / 1e9, 1)}))
+    print(json.dumps({"poly16": p[0], "skew_ns": p[1], "ms": [round(x, 3) for x in res[p]], "best_tflops": round(fl / min(res[p]) / 1e9, 1)}))
