@@ -1,0 +1,428 @@
+// VARIANT v4 of the joint attention kernel: 16 softmax warps (4 per SM sub-partition), two threads per query row, each
+// owning 32 of the 64 columns of a score tile; the pair agrees on reference-max moves through one 64-thread named barrier per
+// tile.  Everything else (TMEM map, MMA issue order, TMA ring) as attn_tcgen05.cu.
+// Joint (text | reference image | video) self-attention forward for sm_100a, head_dim 64, no mask.
+//
+// One CTA owns one (batch, head) and TWO 128-row query tiles (256 query rows) and streams all S keys in 64-key tiles.
+//
+//   warp 0        : TMA producer   — K(t),V(t) tiles through a KV_STAGES-deep mbarrier ring (no Q in shared memory)
+//   warp 1        : tcgen05.mma issuer (single thread); BOTH operands A come from TMEM:
+//                     S_q(t)  = Q_q K(t)^T        TS-MMA  M128 N64 K64   -> TMEM S[q][t&1]  (fp32, double buffered)
+//                     O_q    += P_q(t) V(t)       TS-MMA  M128 N64 K64   -> TMEM O[q]       (fp32)
+//                   V is consumed straight from its [key][d] TMA layout as an MN-major B operand.
+//   warps 4..7    : softmax warpgroup for query tile 0   (one thread = one query row = one TMEM lane)
+//   warps 8..11   : softmax warpgroup for query tile 1
+//
+// Round-1 profile of the previous design (128-key tiles, P aliased onto S): XU pipe 70 %, tensor pipe 35 %, and the
+// softmax warps spent 36 % of their samples waiting for S(t+1), which could only be issued after P(t) had been
+// consumed.  Here S is double buffered and issued ONE TILE AHEAD of the PV product, so the softmax warps (the
+// MUFU-bound resource at head_dim 64: 16 ex2/clk/SM vs 8192 MMA flop/clk/SM) never wait for the tensor pipe:
+//
+//   tensor queue:   S0(t+1) S1(t+1) | PV0(t) PV1(t) | S0(t+2) S1(t+2) | PV0(t+1) ...
+//
+// Softmax (exp2 domain, FA-style online form) with three throughput measures, each taken from
+// tools/microbench_softmax.cu on B200 (profiles/r01_microbench.md):
+//   * no per-tile row max: the running reference m_ref only has to keep 2^(x - m_ref) inside fp32/bf16 range, so it
+//     is moved (and O, l rescaled in TMEM by the owning thread) only when a probability would exceed 2^64 — detected
+//     from the row-sum (inf/huge) and from the polynomial lanes' arguments; tile 0 takes the exact-max path;
+//   * packed fma.rn.f32x2 / add.rn.f32x2 (full rate on sm_100) for the exponent arguments and the row sums;
+//   * POLY of every 8 exponentials are evaluated on the FMA pipe (Cody-Waite split + degree-3 minimax, rel. error
+//     7.5e-5, far below the bf16 rounding of P) instead of MUFU.EX2.
+//
+// TMEM columns (512): Q0 0 | Q1 32 | P0 64 | P1 96 | S[0][0] 128 | S[0][1] 192 | S[1][0] 256 | S[1][1] 320 | O0 384 | O1 448
+//
+// Global layout: qkv [B, S, 3*H*64] (q|k|v, heads contiguous) read through ONE 4-D tensor map {64, 3H, S, B};
+// out [B, S, H*64].  Key rows >= S are zero-filled by TMA and masked to -inf; query rows >= S are not stored.
+#include "common.cuh"
+#include "host_util.h"
+#include "s2v_b200.h"
+
+namespace s2v { namespace v4 {
+
+constexpr int ATT_D = 64;
+constexpr int ATT_BQ = 128;         // rows per query tile (UMMA M)
+constexpr int ATT_QTILES = 2;       // query tiles per CTA
+constexpr int ATT_BK = 64;          // keys per tile
+constexpr int ATT_STAGES = 8;       // K/V ring depth
+constexpr int ATT_THREADS = 640;    // 4 control warps + 16 softmax warps (two threads per query row)
+constexpr int ATT_POLY16_DEFAULT = 1;  // of every 8 PAIRS (16 exponentials), how many pairs run on the FMA pipe
+constexpr uint32_t ATT_TILE_BYTES = ATT_BK * ATT_D * 2;  // 8 KB
+constexpr uint32_t ATT_SMEM_BYTES = 2 * ATT_STAGES * ATT_TILE_BYTES + 1024 + 256;
+constexpr float ATT_P_LIMIT_LOG2 = 64.0f;     // probabilities are kept below 2^64 relative to the reference max
+constexpr float ATT_SUM_LIMIT = 1.8446744e19f;  // 2^64
+
+constexpr uint32_t TM_Q = 0, TM_P = 64, TM_S = 128, TM_O = 384;  // Q_q at q*32, P_q at 64+q*32, S[q][b] at 128+q*128+b*64, O_q at 384+q*64
+
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// 2^x for a packed pair (x <= 127): clamp below, round-to-nearest split x = n + f, degree-3 minimax of 2^f on
+// [-0.5, 0.5], exponent spliced in with an integer shift-add.  `xmax` tracks the largest argument seen (overflow guard).
+__device__ __forceinline__ void exp2_poly2(uint64_t X, float& r0, float& r1, float& xmax) {
+    const float MAGIC = 12582912.0f;  // 1.5 * 2^23: (x + MAGIC) holds round(x) in its low mantissa bits
+    float x0, x1;
+    unpack2(X, x0, x1);
+    xmax = fmax3(xmax, x0, x1);
+    x0 = fmaxf(x0, -125.0f);
+    x1 = fmaxf(x1, -125.0f);
+    X = pack2(x0, x1);
+    const uint64_t T = fadd2(X, pack2(MAGIC, MAGIC));
+    const uint64_t NF = fadd2(T, pack2(-MAGIC, -MAGIC));
+    const uint64_t F = ffma2(NF, pack2(-1.0f, -1.0f), X);
+    uint64_t P = ffma2(pack2(0.05517166f, 0.05517166f), F, pack2(0.24261112f, 0.24261112f));
+    P = ffma2(P, F, pack2(0.69326099f, 0.69326099f));
+    P = ffma2(P, F, pack2(0.99992807f, 0.99992807f));
+    float p0, p1, t0, t1;
+    unpack2(P, p0, p1);
+    unpack2(T, t0, t1);
+    r0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+    r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
+
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int POLY16>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H,
+                   float scale_log2, int skew_ns) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;                                     // STAGES x 8 KB
+    uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;         // STAGES x 8 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_STAGES * ATT_TILE_BYTES);
+    uint64_t* kv_full = bars;                     // STAGES
+    uint64_t* kv_empty = kv_full + ATT_STAGES;    // STAGES
+    uint64_t* s_full = kv_empty + ATT_STAGES;     // 4: [q][buf]
+    uint64_t* p_ready = s_full + 4;               // 2
+    uint64_t* p_free = p_ready + 2;               // 2
+    uint64_t* q_ready = p_free + 2;               // 1
+    uint64_t* o_final = q_ready + 1;              // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
+    int* redo_flag = reinterpret_cast<int*>(tmem_slot + 2);            // 8: one per warp pair
+    float* xchg = reinterpret_cast<float*>(redo_flag + 8);             // [256 rows][2 halves]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int qblk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+    const int q_row0 = qblk * (ATT_BQ * ATT_QTILES);
+    const int n_kv = (S + ATT_BK - 1) / ATT_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        for (int s = 0; s < ATT_STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+        for (int q = 0; q < 2; ++q) {
+            mbar_init(&p_ready[q], 8);  // one arrive per softmax warp
+            mbar_init(&p_free[q], 1);
+        }
+        mbar_init(q_ready, 16);
+        mbar_init(o_final, 1);
+        for (int i = 0; i < 8; ++i) redo_flag[i] = 0;
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        setmaxnreg_dec<40>();
+        if (warp == 0) {
+            if (lane == 0) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int t = 0; t < n_kv; ++t) {
+                    mbar_wait(&kv_empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+                    tma_load_4d(&tmQKV, &kv_full[stage], sK + stage * ATT_TILE_BYTES, 0, H + head, t * ATT_BK, batch);
+                    tma_load_4d(&tmQKV, &kv_full[stage], sV + stage * ATT_TILE_BYTES, 0, 2 * H + head, t * ATT_BK, batch);
+                    if (++stage == ATT_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BK, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_D, 0, 1);
+            auto issue_s = [&](int q, int stage, int buf) {
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + stage * ATT_TILE_BYTES), 16, 1024);
+#pragma unroll
+                for (int k = 0; k < ATT_D / 16; ++k)
+                    umma_ts(tmem_base + TM_S + q * 128 + buf * 64, tmem_base + TM_Q + q * 32 + k * 8, bdesc + uint64_t(k * 2),
+                            idesc_s, k != 0);
+            };
+            auto issue_pv = [&](int q, int stage, bool accumulate) {
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + stage * ATT_TILE_BYTES), 1024, 1024);
+#pragma unroll
+                for (int k = 0; k < ATT_BK / 16; ++k)
+                    umma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_P + q * 32 + k * 8, bdesc + uint64_t(k * 128), idesc_o,
+                            (accumulate || k != 0) ? 1u : 0u);
+            };
+            if (elect_one()) {
+                mbar_wait(q_ready, 0);
+                mbar_wait(&kv_full[0], 0);
+                tc_fence_after();
+                issue_s(0, 0, 0);
+                umma_commit(&s_full[0]);
+                issue_s(1, 0, 0);
+                umma_commit(&s_full[2]);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int t = 0; t < n_kv; ++t) {
+                    int nstage = stage + 1;
+                    uint32_t nphase = phase;
+                    if (nstage == ATT_STAGES) {
+                        nstage = 0;
+                        nphase ^= 1;
+                    }
+                    if (t + 1 < n_kv) {
+                        mbar_wait(&kv_full[nstage], nphase);
+                        tc_fence_after();
+                        const int nb = (t + 1) & 1;
+                        issue_s(0, nstage, nb);
+                        umma_commit(&s_full[nb]);
+                        issue_s(1, nstage, nb);
+                        umma_commit(&s_full[2 + nb]);
+                    }
+                    mbar_wait(&p_ready[0], t & 1);
+                    tc_fence_after();
+                    issue_pv(0, stage, t != 0);
+                    umma_commit(&p_free[0]);
+                    mbar_wait(&p_ready[1], t & 1);
+                    tc_fence_after();
+                    issue_pv(1, stage, t != 0);
+                    umma_commit(&p_free[1]);
+                    umma_commit(&kv_empty[stage]);
+                    if (t + 1 == n_kv) umma_commit(o_final);
+                    stage = nstage;
+                    phase = nphase;
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        // -------------------------------------------------------------------- softmax: 16 warps, two threads per query row
+        setmaxnreg_inc<104>();   // pool: (96-40)*128 = 7168 regs released >= (104-96)*512 = 4096 requested
+        const int sw = warp - 4;
+        const int lq = sw & 3;                  // TMEM lane quarter (== warp % 4)
+        const int half = (sw >> 2) & 1;         // which 32 of the 64 score columns
+        const int q = sw >> 3;                  // query tile
+        const int pair = q * 4 + lq;            // named barrier 1 + pair joins the two halves of the same 32 rows
+        const uint32_t lane_off = uint32_t(lq * 32) << 16;
+        const uint32_t tSb = tmem_base + lane_off + TM_S + q * 128 + half * 32;
+        const uint32_t tP = tmem_base + lane_off + TM_P + q * 32 + half * 16;
+        const uint32_t tO = tmem_base + lane_off + TM_O + q * 64 + half * 32;
+        const int lrow = q * ATT_BQ + lq * 32 + lane;     // row inside the CTA
+        const int row = q_row0 + lrow;
+
+        {   // this thread's half of the query row -> TMEM (A operand of S = Q K^T)
+            uint32_t qr[16];
+            if (row < S) {
+                const uint4* src = reinterpret_cast<const uint4*>(qkv + ((long long)batch * S + row) * (long long)(3 * H * ATT_D) +
+                                                                  head * ATT_D + half * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 v = __ldg(src + i);
+                    qr[4 * i] = v.x; qr[4 * i + 1] = v.y; qr[4 * i + 2] = v.z; qr[4 * i + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) qr[i] = 0u;
+            }
+            tmem_st16(tmem_base + lane_off + TM_Q + q * 32 + half * 16, qr);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_ready);
+        }
+        if (q == 1 && skew_ns > 0) __nanosleep(skew_ns);
+
+        float m_ref = -INFINITY;   // reference max (raw score units), identical in both threads of a row
+        float mneg = 0.f;
+        float l_sum = 0.f;         // this thread's half of the row sum
+        const uint64_t C2 = pack2(scale_log2, scale_log2);
+
+        for (int t = 0; t < n_kv; ++t) {
+            const int buf = t & 1;
+            mbar_wait(&s_full[q * 2 + buf], (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t s[32];
+            tmem_ld32(tSb + buf * 64, s);
+            tmem_ld_wait();
+            const int valid = S - t * ATT_BK - half * 32;  // keys valid among this thread's 32 columns
+            if (valid < 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i >= valid) s[i] = __float_as_uint(-INFINITY);
+            }
+            uint32_t pk[16];
+            float tsum = 0.f;
+            if (t != 0) {
+                const uint64_t M2 = pack2(mneg, mneg);
+                uint64_t acc0 = 0ull, acc1 = 0ull;
+                float xmax = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const uint64_t X = ffma2(pack2(__uint_as_float(s[i + 2 * h]), __uint_as_float(s[i + 2 * h + 1])), C2, M2);
+                        float p0, p1;
+                        if (((i >> 3) & 1) * 4 + h < POLY16) {
+                            exp2_poly2(X, p0, p1, xmax);
+                        } else {
+                            float x0, x1;
+                            unpack2(X, x0, x1);
+                            p0 = ex2_approx(x0);
+                            p1 = ex2_approx(x1);
+                        }
+                        if (h & 1) acc1 = fadd2(acc1, pack2(p0, p1)); else acc0 = fadd2(acc0, pack2(p0, p1));
+                        pk[i / 2 + h] = pack_bf16x2(p0, p1);
+                    }
+                }
+                float a, b, c, d;
+                unpack2(acc0, a, b);
+                unpack2(acc1, c, d);
+                tsum = (a + b) + (c + d);
+                const bool bad = !(tsum < ATT_SUM_LIMIT) || (xmax > ATT_P_LIMIT_LOG2);
+                if (__any_sync(0xffffffffu, bad) && lane == 0) redo_flag[pair] = 1;
+            }
+            pair_sync(1 + pair);                                   // both halves have published their verdict
+            const bool redo = (t == 0) || (redo_flag[pair] != 0);
+            if (t != 0) {
+                mbar_wait(&p_free[q], (t - 1) & 1);                // PV_q(t-1) has consumed P_q(t-1) and left O_q quiescent
+                tc_fence_after();
+            }
+            if (redo) {
+                // ---- exact-max path (tile 0, or a probability would leave the 2^64 window): both halves move the reference
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+                    mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+                }
+                xchg[lrow * 2 + half] = fmaxf(mx0, mx1);
+                pair_sync(1 + pair);
+                const float m_new = fmaxf(m_ref, fmaxf(xchg[lrow * 2], xchg[lrow * 2 + 1]));
+                if (half == 0 && lane == 0) redo_flag[pair] = 0;   // every reader of the flag is past the barrier above
+                if (t != 0) {
+                    const float factor = ex2_approx((m_ref - m_new) * scale_log2);   // 1 when the reference does not move
+                    l_sum *= factor;
+                    uint32_t o[32];
+                    tmem_ld32(tO, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                    tmem_st32(tO, o);
+                }
+                m_ref = m_new;
+                mneg = -m_new * scale_log2;
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, mneg));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg));
+                    a0 += p0;
+                    a1 += p1;
+                    pk[i / 2] = pack_bf16x2(p0, p1);
+                }
+                tsum = a0 + a1;
+                pair_sync(1 + pair);                               // the flag is clear and xchg reusable before anyone runs ahead
+            }
+            l_sum += tsum;
+            tmem_st16(tP, pk);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[q]);
+        }
+        // ---- epilogue: (O / l) -> bf16 -> global; the row sum is the sum of the two halves
+        xchg[lrow * 2 + half] = l_sum;
+        pair_sync(1 + pair);
+        const float inv = 1.0f / (xchg[lrow * 2] + xchg[lrow * 2 + 1]);
+        mbar_wait(o_final, 0);
+        tc_fence_after();
+        bf16* orow = out + ((long long)batch * S + row) * (long long)(H * ATT_D) + head * ATT_D + half * 32;
+        uint32_t o[32];
+        tmem_ld32(tO, o);
+        tmem_ld_wait();
+        if (row < S) {
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+                uint4 w;
+                w.x = pack_bf16x2(__uint_as_float(o[g8 * 8 + 0]) * inv, __uint_as_float(o[g8 * 8 + 1]) * inv);
+                w.y = pack_bf16x2(__uint_as_float(o[g8 * 8 + 2]) * inv, __uint_as_float(o[g8 * 8 + 3]) * inv);
+                w.z = pack_bf16x2(__uint_as_float(o[g8 * 8 + 4]) * inv, __uint_as_float(o[g8 * 8 + 5]) * inv);
+                w.w = pack_bf16x2(__uint_as_float(o[g8 * 8 + 6]) * inv, __uint_as_float(o[g8 * 8 + 7]) * inv);
+                *reinterpret_cast<uint4*>(orow + g8 * 8) = w;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+} }  // namespace s2v::v4
+
+using namespace s2v;
+using namespace s2v::v4;
+
+extern "C" int s2v_attn_fwd_v4(const void* qkv, void* o, int32_t B, int32_t S, int32_t H, float softmax_scale, int32_t poly16,
+                               int32_t skew_ns, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!qkv || !o) return set_error(S2V_E_BADARG, "s2v_attn_fwd_v4: null pointer");
+    if (B <= 0 || S <= 0 || H <= 0 || B > 65535 || H > 65535) return set_error(S2V_E_BADARG, "s2v_attn_fwd_v4: bad problem");
+    int rc = ensure_device();
+    if (rc) return rc;
+    CUtensorMap tm;
+    const uint64_t row_bytes = (uint64_t)3 * H * ATT_D * 2;
+    const uint64_t dims[4] = {(uint64_t)ATT_D, (uint64_t)3 * H, (uint64_t)S, (uint64_t)B};
+    const uint64_t strides[4] = {2, (uint64_t)ATT_D * 2, row_bytes, row_bytes * (uint64_t)S};
+    const uint32_t box[4] = {ATT_D, 1, ATT_BK, 1};
+    if ((rc = make_tmap_nd_bf16(&tm, qkv, 4, dims, strides, box))) return rc;
+    using kern_t = void (*)(const CUtensorMap, const bf16*, bf16*, int, int, float, int);
+    static const kern_t kerns[3] = {attn_fwd_kernel_v4<0>, attn_fwd_kernel_v4<1>, attn_fwd_kernel_v4<2>};
+    if (poly16 < 0 || poly16 > 2) return set_error(S2V_E_BADARG, "s2v_attn_fwd_v4: poly16 0..2");
+    const uint32_t smem = ATT_SMEM_BYTES + 2048 + 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        for (int i = 0; i < 3; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn v4)");
+        }
+        attr_done = true;
+    }
+    dim3 grid((S + ATT_BQ * ATT_QTILES - 1) / (ATT_BQ * ATT_QTILES), H, B);
+    kerns[poly16]<<<grid, ATT_THREADS, smem, stream>>>(tm, static_cast<const bf16*>(qkv), static_cast<bf16*>(o), S, H,
+                                                       softmax_scale * 1.4426950408889634f, skew_ns);
+    return check_launch("attn_fwd_kernel_v4");
+}

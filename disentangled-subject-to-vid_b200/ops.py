@@ -6,6 +6,7 @@ allocates nothing unless an output tensor is not supplied, and raises RuntimeErr
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -141,6 +142,12 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: 
     return out
 
 
+# which attention kernel `attention()` launches: "default" (8 softmax warps) or "v4" (16 softmax warps) — both are sm_100a
+# tcgen05 kernels of this library with the same contract; S2V_ATTN_VARIANT selects at import for A/B runs
+ATTN_VARIANT = os.environ.get("S2V_ATTN_VARIANT", "default")
+ATTN_V4_POLY16, ATTN_V4_SKEW_NS = 1, 200
+
+
 def attention(qkv: torch.Tensor, out: torch.Tensor, heads: int, scale: Optional[float] = None) -> torch.Tensor:
     """qkv [B,S,3*H*64] -> out [B,S,H*64] (joint bidirectional attention, head_dim 64)."""
     _chk_bf16(qkv, "qkv")
@@ -150,8 +157,12 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, heads: int, scale: Optional[
         raise RuntimeError("attention: expected contiguous qkv [B,S,3*H*64] and out [B,S,H*64]")
     lib = _lib.load()
     with _timed("s2v_attn_fwd"):
-        _lib.check(lib.s2v_attn_fwd(qkv.data_ptr(), out.data_ptr(), B, S, heads, scale if scale is not None else 0.125, _stream()),
-                   "s2v_attn_fwd")
+        if ATTN_VARIANT == "v4":
+            _lib.check(lib.s2v_attn_fwd_v4(qkv.data_ptr(), out.data_ptr(), B, S, heads, scale if scale is not None else 0.125,
+                                           ATTN_V4_POLY16, ATTN_V4_SKEW_NS, _stream()), "s2v_attn_fwd_v4")
+        else:
+            _lib.check(lib.s2v_attn_fwd(qkv.data_ptr(), out.data_ptr(), B, S, heads, scale if scale is not None else 0.125, _stream()),
+                       "s2v_attn_fwd")
     return out
 
 

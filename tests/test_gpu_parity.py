@@ -335,3 +335,25 @@ def test_c_abi_error_codes(dev):
     x = torch.zeros(8, 12, device=dev, dtype=BF16)  # K = 12 is not a multiple of 8
     a.x, a.w, a.out, a.M, a.N, a.K, a.ldx, a.ldw, a.ldo = x.data_ptr(), x.data_ptr(), x.data_ptr(), 8, 8, 12, 12, 12, 8
     assert lib.s2v_linear(C.byref(a), None) == -2
+
+
+@pytest.mark.gpu
+def test_attention_v4_variant_matches_default(dev):
+    """The 16-softmax-warp variant (two threads per query row, named-barrier agreement on reference-max moves) computes the
+    same function as the default kernel, including ragged sizes and rows whose maximum jumps by > 2^64."""
+    import torch.nn.functional as F
+    from s2v_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(3)
+    for (B, S, H, boost) in [(1, 1, 1, None), (1, 65, 2, None), (2, 700, 2, 300), (1, 1500, 1, 64)]:
+        qkv = torch.randn(B, S, 3 * H * 64, device=dev)
+        if boost is not None:
+            qkv[:, boost:boost + 3, H * 64:2 * H * 64] *= 40.0
+        qkv = qkv.to(torch.bfloat16)
+        out = torch.full((B, S, H * 64), float("nan"), device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.s2v_attn_fwd_v4(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, 1, 200, torch.cuda.current_stream().cuda_stream),
+                   "s2v_attn_fwd_v4")
+        q, k, v = [t.view(B, S, H, 64).transpose(1, 2).float() for t in qkv.chunk(3, dim=-1)]
+        ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
+        err = float((out.float() - ref).abs().max() / ref.abs().max())
+        assert err < 2e-2, (B, S, H, boost, err)

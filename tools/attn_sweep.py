@@ -40,19 +40,23 @@ for rep in range(3):
         lib.s2v_attn_set_poly16(p[0])
         lib.s2v_attn_set_skew_ns(p[1])
         res[p].append(timed(lambda: ops.attention(qkv, out, H)))
-def v3():
-    _lib.check(lib.s2v_attn_fwd_v3(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, torch.cuda.current_stream().cuda_stream), "v3")
+def v4(poly=1, skew=200):
+    _lib.check(lib.s2v_attn_fwd_v4(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, poly, skew, torch.cuda.current_stream().cuda_stream), "v4")
 
 
-if hasattr(lib, "s2v_attn_fwd_v3"):
+if hasattr(lib, "s2v_attn_fwd_v4"):
     lib.s2v_attn_set_poly16(1); lib.s2v_attn_set_skew_ns(200)
-    ops.attention(qkv, out, H); o_main = out.clone(); v3(); torch.cuda.synchronize()
-    print(json.dumps({"v3_max_abs_diff_vs_main": float((out.float() - o_main.float()).abs().max())}))
-    a, b = [], []
-    for rep in range(4):
+    ops.attention(qkv, out, H); o_main = out.clone(); v4(); torch.cuda.synchronize()
+    print(json.dumps({"v4_max_abs_diff_vs_main": float((out.float() - o_main.float()).abs().max())}))
+    cfgs = [(0, 0), (1, 0), (1, 200), (2, 200), (1, 400)]
+    a, b = [], {c: [] for c in cfgs}
+    for rep in range(3):
         a.append(timed(lambda: ops.attention(qkv, out, H)))
-        b.append(timed(v3))
-    print(json.dumps({"main_ms": [round(x, 3) for x in a], "v3_ms": [round(x, 3) for x in b]}))
+        for c in cfgs:
+            b[c].append(timed(lambda: v4(*c)))
+    print(json.dumps({"main_ms": [round(x, 3) for x in a]}))
+    for c in cfgs:
+        print(json.dumps({"v4 poly16,skew": c, "ms": [round(x, 3) for x in b[c]]}))
 print(json.dumps({"torch_sdpa_ms": [round(x, 3) for x in ref], "tflops": round(fl / min(ref) / 1e9, 1)}))
 for p in vals:
     print(json.dumps({"poly16": p[0], "skew_ns": p[1], "ms": [round(x, 3) for x in res[p]], "best_tflops": round(fl / min(res[p]) / 1e9, 1)}))
