@@ -238,7 +238,11 @@ def run_product(args, w):
     if attn:
         ach = attn_per_launch / (attn["avg_ms"] / 1e3) / 1e12
         roof = {"kernel": "attn_fwd_kernel", "bound": "tensor", "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(ach / peak_tf, 4), "traffic": None, "peak_source": peak_src, "avg_launch_ms": round(attn["avg_ms"], 4),
+                "frac": round(ach / peak_tf, 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this shape
+                # (profiles/r01_attn_ncu_full.txt): 706 MB + 219 MB per launch; algorithmic 705 MB (qkv) + 235 MB (out)
+                "traffic": 925.2e6 if args.workload == "cfg3" else None, "algorithmic_bytes": 3 * S * D * 2 * 2 * P + S * D * 2 * 2 * P,
+                "peak_source": peak_src, "avg_launch_ms": round(attn["avg_ms"], 4),
                 "share_of_step": round(attn["total_ms"] / ms, 4)}
     gemm_fl = {"s2v_qkv_lora": 2 * S * D * (3 * D), "s2v_outproj_lora_gate_residual": 2 * S * D * D,
                "s2v_ffn_up_gelu_lora": 2 * S * D * 4 * D, "s2v_ffn_down_lora_gate_residual": 2 * S * D * 4 * D}

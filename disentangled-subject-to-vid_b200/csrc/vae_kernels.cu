@@ -114,19 +114,31 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
     }
 }
 
-// Stage 2: one block; stats[g] = (mean, rstd) over the group's channels and all stage-1 blocks (fixed summation order).
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int nblk, int C, int G, float count,
-                                   float eps) {
-    const int cpg = C / G;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        double s = 0.0, q = 0.0;
-        for (int b = 0; b < nblk; ++b)
-            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-                s += partial[((long long)b * C + c) * 2];
-                q += partial[((long long)b * C + c) * 2 + 1];
-            }
-        const double mean = s / count;
-        double var = q / count - mean * mean;
+// Stage 2: one 128-thread block per group; stats[g] = (mean, rstd) over the group's channels and all stage-1 blocks.  Each
+// thread sums a fixed strided subset in double, then a fixed-shape tree combines them (deterministic).
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int nblk, int C, int G,
+                                                          float count, float eps) {
+    const int g = blockIdx.x, cpg = C / G, n = nblk * cpg;
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < n; i += 128) {
+        const int b = i / cpg, c = g * cpg + (i - b * cpg);
+        s += partial[((long long)b * C + c) * 2];
+        q += partial[((long long)b * C + c) * 2 + 1];
+    }
+    __shared__ double rs[128], rq[128];
+    rs[threadIdx.x] = s;
+    rq[threadIdx.x] = q;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            rs[threadIdx.x] += rs[threadIdx.x + o];
+            rq[threadIdx.x] += rq[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double mean = rs[0] / count;
+        double var = rq[0] / count - mean * mean;
         var = var < 0.0 ? 0.0 : var;
         stats[g * 2] = (float)mean;
         stats[g * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
@@ -285,7 +297,7 @@ extern "C" int s2v_vae_groupnorm_stats(const void* x, float* partial, float* sta
     nblk = (lines + lpb - 1) / lpb;
     gn_partial_kernel<<<nblk, 256, 0, stream>>>(static_cast<const bf16*>(x), partial, T, H, W, C, lpb);
     if ((rc = check_launch("gn_partial_kernel"))) return rc;
-    gn_finalize_kernel<<<1, 32, 0, stream>>>(partial, stats, nblk, C, G, (float)((double)T * H * W * (C / G)), eps);
+    gn_finalize_kernel<<<G, 128, 0, stream>>>(partial, stats, nblk, C, G, (float)((double)T * H * W * (C / G)), eps);
     return check_launch("gn_finalize_kernel");
 }
 
