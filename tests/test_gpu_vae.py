@@ -131,3 +131,52 @@ def test_decode_batch_and_chain(dev, fix, vae):
         y = m.decode(fix["z"][:, :, :, :4, :6].to(torch.bfloat16).to(dev)).sample
     want = torch.cat([fix["decoder_chain"]["y0"], fix["decoder_chain"]["y1"]], dim=2)
     assert rel(y, want) < 1.5e-2
+
+
+def test_full_pipeline_call_with_vae_vs_oracle(dev):
+    """CustomCogVideoXPipeline.__call__ end to end on the GPU (3 guided steps -> decode_latents -> postprocess 'pt') against
+    the CPU oracle chain (denoise_loop -> decode_latents), i.e. rows P, S, R, T, B, N, A, F, L, O and V in one call."""
+    import s2v_b200
+    from oracle import s2v_oracle as O
+
+    bf16 = torch.bfloat16
+    cfg = O.TransformerConfig(num_attention_heads=2, num_layers=2, time_embed_dim=64, text_embed_dim=64,
+                              use_rotary_positional_embeddings=True, lora_rank=8, lora_alpha=4.0)
+    p16 = {k: v.to(bf16) for k, v in O.synth_params(cfg, seed=5).items()}
+    model = s2v_b200.CogVideoXTransformer3DModel(num_attention_heads=2, num_layers=2, time_embed_dim=64, text_embed_dim=64,
+                                                 use_rotary_positional_embeddings=True).to(bf16)
+    s2v_b200.inject_lora(model, 8, 4.0)
+    mods = dict(model.named_modules())
+    with torch.no_grad():
+        for k, v in p16.items():
+            mod, _, leaf = k.rpartition(".")
+            base, _, ab = mod.rpartition(".")
+            if ab in ("lora_A", "lora_B"):
+                getattr(mods[base], ab)["default"].weight.copy_(v)
+            else:
+                getattr(getattr(mods[mod], "base_layer", mods[mod]), leaf).copy_(v)
+    model = model.to(dev)
+    h, w, Fr = 8, 12, 3
+    vcfg = V.VaeConfig(block_out_channels=(64, 64, 128, 128), layers_per_block=1, sample_height=h * 8, sample_width=w * 8)
+    vp = V.synth_decoder_params(vcfg, seed=9)
+    vae = s2v_b200.AutoencoderKLCogVideoX(block_out_channels=vcfg.block_out_channels, layers_per_block=1, sample_height=h * 8,
+                                          sample_width=w * 8, scaling_factor=vcfg.scaling_factor)
+    vae.load_state_dict(vp)
+    vae = vae.to(bf16).to(dev)
+    g = torch.Generator().manual_seed(6)
+    lat = torch.randn(1, Fr, 16, h, w, generator=g).to(bf16)
+    ref = (0.7 * torch.randn(1, 1, 16, h, w, generator=g)).to(bf16)
+    pe = (0.2 * torch.randn(2, 226, 64, generator=g)).to(bf16)
+    pipe = s2v_b200.CustomCogVideoXPipeline(None, None, model, vae, s2v_b200.CogVideoXDDIMScheduler.for_cogvideox(1.0))
+    frames = pipe(ref_img_states=ref, height=h * 8, width=w * 8, num_frames=(Fr - 1) * 4 + 1, num_inference_steps=3, guidance_scale=6.0,
+                  latents=lat, prompt_embeds=pe[1:], negative_prompt_embeds=pe[:1], output_type="pt", return_dict=False)[0]
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want_lat = O.denoise_loop({k: v.float() for k, v in p16.items()}, cfg, lat.float(), pe.float(), ref.float(), h * 8, w * 8,
+                                  num_inference_steps=3, guidance_scale=6.0, snr_shift_scale=1.0)
+        want = V.decode_latents(vp, vcfg, want_lat, use_tiling=False)
+    want = (want[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)           # video_processor.py:89-113
+    assert frames.shape[1:] == want.shape and frames.shape[0] == 1
+    err = float((frames[0].float().cpu() - want).abs().mean())
+    print(f"full pipeline: mean abs pixel error vs fp32 CPU oracle {err:.3e} (pixels in [0, 1])")
+    assert err < 2e-2
