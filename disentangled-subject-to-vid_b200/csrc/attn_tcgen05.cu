@@ -26,7 +26,8 @@
 //   * POLY of every 8 exponentials are evaluated on the FMA pipe (Cody-Waite split + degree-3 minimax, rel. error
 //     7.5e-5, far below the bf16 rounding of P) instead of MUFU.EX2.
 //
-// TMEM columns (512): Q0 0 | Q1 32 | P0 64 | P1 96 | S[0][0] 128 | S[0][1] 192 | S[1][0] 256 | S[1][1] 320 | O0 384 | O1 448
+// TMEM columns (512): Q0 0 | Q1 32 | (64 free) | S[0][0] 128 | S[0][1] 192 | S[1][0] 256 | S[1][1] 320 | O0 384 | O1 448;
+// P_q(t) (bf16) overwrites the first 32 columns of its own score buffer S[q][t&1] once the scores are in registers
 //
 // Global layout: qkv [B, S, 3*H*64] (q|k|v, heads contiguous) read through ONE 4-D tensor map {64, 3H, S, B};
 // out [B, S, H*64].  Key rows >= S are zero-filled by TMA and masked to -inf; query rows >= S are not stored.
@@ -48,7 +49,7 @@ constexpr uint32_t ATT_SMEM_BYTES = 2 * ATT_STAGES * ATT_TILE_BYTES + 1024 + 256
 constexpr float ATT_P_LIMIT_LOG2 = 64.0f;     // probabilities are kept below 2^64 relative to the reference max
 constexpr float ATT_SUM_LIMIT = 1.8446744e19f;  // 2^64
 
-constexpr uint32_t TM_Q = 0, TM_P = 64, TM_S = 128, TM_O = 384;  // Q_q at q*32, P_q at 64+q*32, S[q][b] at 128+q*128+b*64, O_q at 384+q*64
+constexpr uint32_t TM_Q = 0, TM_S = 128, TM_O = 384;  // Q_q at q*32, S[q][b] at 128+q*128+b*64 (P(t) over its first 32 columns), O_q at 384+q*64
 
 __device__ __forceinline__ uint64_t pack2(float a, float b) {
     uint64_t r;
@@ -107,8 +108,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
     uint64_t* kv_full = bars;                     // STAGES
     uint64_t* kv_empty = kv_full + ATT_STAGES;    // STAGES
     uint64_t* s_full = kv_empty + ATT_STAGES;     // 4: [q][buf]
-    uint64_t* p_ready = s_full + 4;               // 2
-    uint64_t* p_free = p_ready + 2;               // 2
+    uint64_t* p_ready = s_full + 4;               // 4: [q][tile parity]
+    uint64_t* p_free = p_ready + 4;               // 2
     uint64_t* q_ready = p_free + 2;               // 1
     uint64_t* o_final = q_ready + 1;              // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
@@ -126,10 +127,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
             mbar_init(&kv_empty[s], 1);
         }
         for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
-        for (int q = 0; q < 2; ++q) {
-            mbar_init(&p_ready[q], 4);  // one arrive per softmax warp
-            mbar_init(&p_free[q], 1);
-        }
+        // p_ready is double buffered by tile parity: without a per-tile p_free wait a fast softmax warp may finish tile t+1
+        // before a slow one has arrived for tile t (it cannot get further: S(t+2) is only issued after p_ready(t)), and
+        // two arrivals of one warp must never land in the same barrier phase.
+        for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], 4);  // one arrive per softmax warp of the query tile
+        for (int q = 0; q < 2; ++q) mbar_init(&p_free[q], 1);
         mbar_init(q_ready, 8);
         mbar_init(o_final, 1);
         fence_barrier_init();
@@ -164,17 +166,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
             constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_D, 0, 1);    // O += P V    (A in TMEM, B MN-major)
             auto issue_s = [&](int q, int stage, int buf) {
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + stage * ATT_TILE_BYTES), 16, 1024);
+                if (skew_ns & (1 << 30)) return;   // timing experiment: softmax side without tensor-core activity (results invalid)
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)
                     umma_ts(tmem_base + TM_S + q * 128 + buf * 64, tmem_base + TM_Q + q * 32 + k * 8, bdesc + uint64_t(k * 2),
                             idesc_s, k != 0);
             };
-            auto issue_pv = [&](int q, int stage, bool accumulate) {
+            auto issue_pv = [&](int q, int stage, bool accumulate, int t) {
                 // V tile [64 keys][64 d]: 16 keys per MMA = two 8-row groups = 2048 bytes
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + stage * ATT_TILE_BYTES), 1024, 1024);
+                if (skew_ns & (1 << 30)) return;
 #pragma unroll
                 for (int k = 0; k < ATT_BK / 16; ++k)
-                    umma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_P + q * 32 + k * 8, bdesc + uint64_t(k * 128), idesc_o,
+                    umma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_S + q * 128 + (t & 1) * 64 + k * 8, bdesc + uint64_t(k * 128), idesc_o,
                             (accumulate || k != 0) ? 1u : 0u);
             };
             // The whole issue loop runs in ONE elected thread: with `elect.sync` the compiler knows a single lane is
@@ -208,13 +212,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                         umma_commit(&s_full[2 + nb]);
                     }
                     // ---- O_q += P_q(t) V(t)
-                    mbar_wait(&p_ready[0], t & 1);
+                    mbar_wait(&p_ready[t & 1], (t >> 1) & 1);
                     tc_fence_after();
-                    issue_pv(0, stage, t != 0);
+                    issue_pv(0, stage, t != 0, t);
                     umma_commit(&p_free[0]);
-                    mbar_wait(&p_ready[1], t & 1);
+                    mbar_wait(&p_ready[2 + (t & 1)], (t >> 1) & 1);
                     tc_fence_after();
-                    issue_pv(1, stage, t != 0);
+                    issue_pv(1, stage, t != 0, t);
                     umma_commit(&p_free[1]);
                     umma_commit(&kv_empty[stage]);  // every MMA reading K(t)/V(t) has been issued before this point
                     if (t + 1 == n_kv) umma_commit(o_final);
@@ -231,7 +235,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
         const int lq = warp & 3;                // TMEM lane quarter
         const uint32_t lane_off = uint32_t(lq * 32) << 16;
         const uint32_t tSb = tmem_base + lane_off + TM_S + q * 128;
-        const uint32_t tP = tmem_base + lane_off + TM_P + q * 32;
         const uint32_t tO = tmem_base + lane_off + TM_O + q * 64;
         const int row = q_row0 + q * ATT_BQ + lq * 32 + lane;
 
@@ -259,7 +262,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
 
         // Start the second query tile's softmax half a tile late: with both warpgroups in lock-step they fight for the
         // exponential unit during the same phase and leave it idle during their common load/store phases.
-        if (q == 1 && skew_ns > 0) __nanosleep(skew_ns);
+        if (q == 1 && (skew_ns & 0xfffff) > 0) __nanosleep(skew_ns & 0xfffff);
 
         float m_ref = -INFINITY;   // reference max (raw score units) used in the exponent
         float mneg = 0.f;          // -m_ref * scale_log2
@@ -317,8 +320,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 const bool bad = !(tsum < ATT_SUM_LIMIT) || (xmax > ATT_P_LIMIT_LOG2);
                 redo = __any_sync(0xffffffffu, bad);
             }
-            if (t != 0) {
-                mbar_wait(&p_free[q], (t - 1) & 1);   // PV_q(t-1) has consumed P_q(t-1) and left O_q quiescent
+            // P(t) is stored over the first 32 columns of its own score buffer S[q][t&1] (dead once it is in registers).  That
+            // buffer's previous tenant P(t-2) was consumed before S(t) could be written (the tensor pipe executes in order),
+            // so the store needs no barrier wait; only the rare O rescale must know that PV_q(t-1) has finished.
+            if (t != 0 && redo) {
+                mbar_wait(&p_free[q], (t - 1) & 1);
                 tc_fence_after();
             }
             if (redo) {
@@ -358,11 +364,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 tsum = a0 + a1;
             }
             l_sum += tsum;
-            tmem_st32(tP, pk);
+            tmem_st32(tSb + buf * 64, pk);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_ready[q]);
+            if (lane == 0) mbar_arrive(&p_ready[q * 2 + buf]);
         }
         // ---- epilogue: O / l -> bf16 -> global
         mbar_wait(o_final, 0);
@@ -404,7 +410,7 @@ static int g_att_poly16 = ATT_POLY16_DEFAULT;
 static int g_att_skew_ns = 200;   // measured +4 % on B200 (tools/attn_sweep.py 1:0 1:150 1:300 ...)
 
 extern "C" int s2v_attn_set_skew_ns(int32_t ns) {
-    if (ns < 0 || ns > 100000) return set_error(S2V_E_BADARG, "s2v_attn_set_skew_ns: expected 0..100000");
+    if (ns < 0 || ((ns & 0xfffff) > 100000)) return set_error(S2V_E_BADARG, "s2v_attn_set_skew_ns: expected 0..100000");
     g_att_skew_ns = ns;
     return 0;
 }

@@ -1,0 +1,19 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, json
+from s2v_b200 import _lib, ops
+B, S, H = 2, 19126, 48
+qkv = torch.randn(B, S, 3 * H * 64, device="cuda").to(torch.bfloat16)
+out = torch.empty(B, S, H * 64, device="cuda", dtype=torch.bfloat16)
+lib = _lib.load()
+def timed(iters=4):
+    ops.attention(qkv, out, H); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): ops.attention(qkv, out, H)
+    e1.record(); torch.cuda.synchronize()
+    return round(e0.elapsed_time(e1) / iters, 3)
+for rep in range(2):
+    lib.s2v_attn_set_skew_ns(200); a = timed()
+    lib.s2v_attn_set_skew_ns(200 | (1 << 30)); b = timed()
+    print(json.dumps({"with_mma_ms": a, "softmax_only_no_mma_ms": b}))

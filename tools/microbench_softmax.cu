@@ -66,7 +66,7 @@ __device__ __forceinline__ void exp2_poly2(uint64_t X, float& r0, float& r1) {
     r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-template <int MODE, int POLY, int WARPS>
+template <int MODE, int POLY, int WARPS, bool TM = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) softmax_bench(const float* __restrict__ in, float* out, long long* cycles, int iters,
                                                         float c, float m0) {
     extern __shared__ uint4 sm[];
@@ -77,10 +77,39 @@ __global__ void __launch_bounds__(WARPS * 32, 1) softmax_bench(const float* __re
     float lsum = 0.f;
     float mneg = m0;
     uint4* dst = sm + threadIdx.x * 16;
+    __shared__ uint32_t tm_slot;
+    uint32_t tbase = 0;
+    if (TM) {
+        if (threadIdx.x < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tm_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int w = threadIdx.x >> 5;
+        tbase = tm_slot + (uint32_t((w & 3) * 32) << 16) + (w >> 2) * (512 / (WARPS / 4));
+    }
     __syncthreads();
     const long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
+        if (TM) {   // the score tile arrives through tcgen05.ld, as in the attention kernel (values are discarded: timing only)
+#pragma unroll
+            for (int c = 0; c < E / 32; ++c) {
+                uint32_t v[32];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                               "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                               "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                               "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                             : "r"(tbase + (c % 2) * 32)
+                             : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                mneg += __uint_as_float(v[it & 31] & 1u);     // keep the load alive (adds 0 or ~1e-45)
+            }
+        }
         if (MODE == 0) {
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -136,15 +165,35 @@ __global__ void __launch_bounds__(WARPS * 32, 1) softmax_bench(const float* __re
             unpack2(acc1, cc, d);
             lsum += (a + b) + (cc + d);
         }
+        if (TM) {   // probabilities leave through tcgen05.st
 #pragma unroll
-        for (int i = 0; i < E / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            for (int c = 0; c < E / 64; ++c) {
+                const uint32_t* r = &pk[c * 32];
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                             "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                             ::"r"(tbase + 64), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                               "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+                               "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
+                               "r"(r[29]), "r"(r[30]), "r"(r[31])
+                             : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int i = 0; i < E / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
     }
     const long long t1 = clock64();
     out[blockIdx.x * blockDim.x + threadIdx.x] = lsum + mneg + __uint_as_float(dst[3].x);
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_slot), "r"(512) : "memory");
+    }
 }
 
-template <int MODE, int POLY, int WARPS>
+template <int MODE, int POLY, int WARPS, bool TM = false>
 void run(const char* name) {
     const int warps = WARPS, blocks = 148, threads = warps * 32, iters = 2000;
     float *in, *out;
@@ -155,7 +204,7 @@ void run(const char* name) {
     float h[4096];
     for (int i = 0; i < 4096; ++i) h[i] = -3.0f + 0.0011f * i;
     cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
-    auto k = softmax_bench<MODE, POLY, WARPS>;
+    auto k = softmax_bench<MODE, POLY, WARPS, TM>;
     const int smem = threads * 16 * sizeof(uint4);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     k<<<blocks, threads, smem>>>(in, out, cyc, iters, 0.18f, -0.5f);
@@ -169,8 +218,8 @@ void run(const char* name) {
     avg /= blocks;
     // cycles for the SM to finish one "iteration" of 8 row-tiles' worth of work (= 2 Q tiles x 128 rows = 8 warps x 128 elems)
     const double per_iter8 = avg / iters;   // every variant processes 8 x 32 x 128 elements per SM per iteration
-    printf("{\"variant\": \"%s\", \"warps\": %d, \"cycles_per_2x128x128_tile_pair\": %.1f, \"cycles_per_elem_per_smsp\": %.3f, \"err\": \"%s\"}\n",
-           name, warps, per_iter8, per_iter8 / 256.0, cudaGetErrorString(e));
+    printf("{\"variant\": \"%s%s\", \"warps\": %d, \"cycles_per_2x128x128_tile_pair\": %.1f, \"cycles_per_elem_per_smsp\": %.3f, \"err\": \"%s\"}\n",
+           name, TM ? " + tcgen05.ld/st traffic" : "", warps, per_iter8, per_iter8 / 256.0, cudaGetErrorString(e));
     cudaFree(in); cudaFree(out); cudaFree(cyc);
 }
 
@@ -212,5 +261,9 @@ int main() {
     run<1, 8, 16>("nomax packed, poly 8/8");
     run<2, 2, 16>("max3 packed, poly 2/8");
     run<2, 4, 16>("max3 packed, poly 4/8");
+    run<1, 0, 8, true>("nomax packed, all MUFU");
+    run<1, 2, 8, true>("nomax packed, poly 2/8");
+    run<1, 0, 16, true>("nomax packed, all MUFU");
+    run<1, 2, 16, true>("nomax packed, poly 2/8");
     return 0;
 }
