@@ -53,6 +53,17 @@ def flops_per_step(w):
     return 2 * w["layers"] * per, 2 * w["layers"] * 4 * S * S * D
 
 
+def config_of(args, w, prompts):
+    """The `config` object both arms print (same workload name for the product and the reference arm)."""
+    n, F, S, D = geometry(w)
+    total_fl, _ = flops_per_step(w)
+    return {"workload": f"{args.workload}: {w['model']}{' + LoRA r=%d' % w['lora'][0] if w['lora'] else ''}, {w['frames']} frames "
+                        f"{w['height']}x{w['width']}, CFG batch 2, {w['layers']} layers, S={S} tokens, one prompt per GPU",
+            "prompts": prompts, "sharding": "prompt (no per-step collective; one all-gather of final latents)",
+            "l2": "inputs larger than L2: 11+ GB weights and 235 MB activations per tensor vs 126 MB L2",
+            "tflop_per_step": round(total_fl / 1e12, 1)}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -253,11 +264,7 @@ def run_product(args, w):
         "metric": "denoising_steps_per_sec", "value": round(value, 4), "unit": "steps/s (one step = one guided update of one 49f 480x720 video)",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w['model']}{' + LoRA r=%d' % w['lora'][0] if w['lora'] else ''}, {w['frames']} frames "
-                               f"{w['height']}x{w['width']}, CFG batch 2, {w['layers']} layers, S={S} tokens, one prompt per GPU",
-                   "prompts": P_total, "sharding": "prompt (no per-step collective; one all-gather of final latents)",
-                   "l2": "inputs larger than L2: 11+ GB weights and 235 MB activations per tensor vs 126 MB L2",
-                   "tflop_per_step": round(total_fl / 1e12, 1)},
+        "config": config_of(args, w, P_total),
         "clocks": clocks,
         "e2e": {"value": round(e2e_v, 4), "unit": "steps/s", "h2d_bytes_per_step": int(lat_h.nbytes + pe_h.nbytes + ref_h.nbytes),
                 "d2h_bytes_per_step": int(out_h.nbytes), "ms_per_step": round(ms_e2e / args.steps, 3)},
@@ -358,8 +365,7 @@ def run_reference(args, w):
             "unit": "steps/s (one step = one guided update of one 49f 480x720 video)", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['model']}, {w['frames']} frames {w['height']}x{w['width']}, CFG batch 2, S={S}",
-                       "tflop_per_step": round(total_fl / 1e12, 1)},
+            "config": config_of(args, w, args.gpus),
             "cpu_baseline": res, "e2e": {"value": res["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

@@ -22,7 +22,7 @@ from .modules import (  # noqa: F401
     attach,
 )
 from .pipeline import CogVideoXPipelineOutput, CustomCogVideoXPipeline  # noqa: F401
-from .scheduler import CogVideoXDDIMScheduler  # noqa: F401
+from .scheduler import CogVideoXDDIMScheduler, CogVideoXDPMScheduler  # noqa: F401
 from .vae import AutoencoderKLCogVideoX, attach_vae  # noqa: F401
 
 __version__ = "0.1.0"

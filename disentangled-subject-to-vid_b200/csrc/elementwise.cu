@@ -365,6 +365,38 @@ __global__ void ddim_step_kernel(const float* __restrict__ v_in, const bf16* __r
     }
 }
 
+// DPM-Solver++ (SDE, multistep) update of CogVideoXDPMScheduler.step (scheduling_dpm_cogvideox.py:383-439) with the
+// reference's rounding points on CUDA: (fp64 scalar) * (bf16 tensor) is an fp32 product rounded to bf16, everything that
+// touches an fp32 tensor stays fp32, left-to-right evaluation, no FMA contraction.
+//   x0   = bf16(sa*x) - sb*v
+//   d    = second_order ? m2*x0 - m3*old_x0 : x0
+//   prev = (bf16(m0*x) - m1*d) + bf16(mn*noise)
+// CFG = true: v = u + g*(t - u) from a bf16 [2, n] model output (uncond first), result rounded to bf16 (the pipe's .to());
+// CFG = false: v is the fp32 model output and prev stays fp32 (the scheduler.step surface).
+template <bool CFG>
+__global__ void dpm_step_kernel(const void* __restrict__ v_in, const bf16* __restrict__ lat, const float* __restrict__ old_x0,
+                                const bf16* __restrict__ noise, void* __restrict__ prev_out, float* __restrict__ x0_out, long long n,
+                                float g, float sa, float sb, float m0, float m1, float m2, float m3, float mn) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v;
+        if (CFG) {
+            const bf16* np = static_cast<const bf16*>(v_in);
+            const float u = __bfloat162float(np[i]), t = __bfloat162float(np[n + i]);
+            v = __fadd_rn(u, __fmul_rn(g, __fsub_rn(t, u)));
+        } else {
+            v = static_cast<const float*>(v_in)[i];
+        }
+        const float x = __bfloat162float(lat[i]);
+        const float x0 = __fsub_rn(round_bf16f(__fmul_rn(sa, x)), __fmul_rn(sb, v));
+        const float d = old_x0 ? __fsub_rn(__fmul_rn(m2, x0), __fmul_rn(m3, old_x0[i])) : x0;
+        const float prev = __fadd_rn(__fsub_rn(round_bf16f(__fmul_rn(m0, x)), __fmul_rn(m1, d)),
+                                     round_bf16f(__fmul_rn(mn, __bfloat162float(noise[i]))));
+        if (CFG) static_cast<bf16*>(prev_out)[i] = __float2bfloat16(prev);
+        else static_cast<float*>(prev_out)[i] = prev;
+        x0_out[i] = x0;
+    }
+}
+
 template <typename F>
 static int dispatch_maxv(int D, F&& f) {
     const int nvec = D / 8;
@@ -507,4 +539,23 @@ extern "C" int s2v_ddim_step(const float* model_output, const void* sample, floa
     ddim_step_kernel<<<ew_grid(n), 256, 0, stream>>>(model_output, static_cast<const bf16*>(sample), prev_out, x0_out, n,
                                                     sqrt_alpha, sqrt_beta, a_coef, b_coef);
     return check_launch("ddim_step_kernel");
+}
+
+extern "C" int s2v_dpm_step(const void* model_output, int32_t cfg_input, const void* sample, const float* old_x0, const void* noise,
+                            void* prev_out, float* x0_out, int64_t n, float guidance, float sqrt_alpha, float sqrt_beta, float m0, float m1,
+                            float m2, float m3, float m_noise, void* stream_) {
+    if (!model_output || !sample || !noise || !prev_out || !x0_out) return set_error(S2V_E_BADARG, "s2v_dpm_step: null pointer");
+    if (n <= 0) return set_error(S2V_E_BADARG, "s2v_dpm_step: empty problem");
+    S2V_PROLOGUE();
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (cfg_input)
+        dpm_step_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(model_output, static_cast<const bf16*>(sample), old_x0,
+                                                                     static_cast<const bf16*>(noise), prev_out, x0_out, n, guidance, sqrt_alpha,
+                                                                     sqrt_beta, m0, m1, m2, m3, m_noise);
+    else
+        dpm_step_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(model_output, static_cast<const bf16*>(sample), old_x0,
+                                                                      static_cast<const bf16*>(noise), prev_out, x0_out, n, guidance, sqrt_alpha,
+                                                                      sqrt_beta, m0, m1, m2, m3, m_noise);
+    return check_launch("dpm_step_kernel");
 }

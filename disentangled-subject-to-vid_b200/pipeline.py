@@ -21,6 +21,7 @@ from typing import Any, Callable, Dict, List, Optional, Tuple, Union
 import torch
 
 from . import ops, tables
+from .scheduler import CogVideoXDPMScheduler  # noqa: F401
 from .scheduler import CogVideoXDDIMScheduler
 
 BF16 = torch.bfloat16
@@ -235,6 +236,7 @@ class CustomCogVideoXPipeline:
         t_dev = torch.tensor(steps_host, device=device, dtype=torch.float32)
         model_in = torch.empty((2 * P,) + tuple(latents.shape[1:]), device=device, dtype=BF16)
         nxt = torch.empty_like(latents)
+        old_pred_original_sample = None
         for i, t in enumerate(steps_host):
             if self.interrupt:
                 break
@@ -245,8 +247,13 @@ class CustomCogVideoXPipeline:
                                           ref_image_rotary_emb=ref_image_rotary_emb, attention_kwargs=attention_kwargs,
                                           return_dict=False, eval=True)[0]
             self._guidance_scale = self._guidance_for_step(guidance_scale, use_dynamic_cfg, i, num_inference_steps)
-            # .float() -> u + g (t - u) -> DDIM step -> .to(bf16), fused and bit-exact
-            self.scheduler.step_cfg(noise_pred.contiguous(), t, latents, self._guidance_scale, out=nxt)
+            # .float() -> u + g (t - u) -> scheduler step -> .to(bf16), fused and bit-exact
+            if isinstance(self.scheduler, CogVideoXDPMScheduler):   # S/custom_cogvideox_pipe.py:288-295
+                _, old_pred_original_sample = self.scheduler.step_cfg_dpm(
+                    noise_pred.contiguous(), old_pred_original_sample, t, steps_host[i - 1] if i > 0 else None, latents,
+                    self._guidance_scale, generator=generator, out=nxt)
+            else:
+                self.scheduler.step_cfg(noise_pred.contiguous(), t, latents, self._guidance_scale, out=nxt)
             latents, nxt = nxt, latents
             if callback_on_step_end is not None:
                 kw = {"latents": latents, "prompt_embeds": prompt_embeds, "negative_prompt_embeds": negative_prompt_embeds}

@@ -15,6 +15,7 @@ from typing import Optional, Tuple, Union
 import numpy as np
 import torch
 
+from . import _lib as _lib_mod
 from . import ops
 
 
@@ -167,3 +168,89 @@ class CogVideoXDDIMScheduler:
         sa, sb, a, b = self.coefficients(self._as_int(timestep))
         out = torch.empty_like(latents) if out is None else out
         return ops.cfg_ddim_step(noise_pred, latents, out, float(guidance), sa, sb, a, b)
+
+
+class CogVideoXDPMScheduler(CogVideoXDDIMScheduler):
+    """DPM-Solver++ (SDE, second-order multistep) variant the pipeline also accepts (D/schedulers/scheduling_dpm_cogvideox.py;
+    loop branch S/custom_cogvideox_pipe.py:288-295).  Same beta / SNR-shift / zero-terminal-SNR tables and timestep spacing as
+    the DDIM scheduler; the update draws Gaussian noise (stochastic), with the reference's draw protocol so that a given
+    `torch.Generator` yields the same latents: one bf16 `randn` per step, a second one on second-order steps (the second is
+    the one that is used, :421-433)."""
+
+    def dpm_coefficients(self, timestep: int, timestep_back: Optional[int]):
+        """(sa, sb, m0, m1, m2, m3, m_noise, second_order) — get_variables / get_mult (:306-328) in fp64 0-dim tensors exactly as
+        the reference evaluates them, returned as the fp32 values the device multiplies with."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        if self.config.prediction_type != "v_prediction":
+            raise NotImplementedError("the B200 path implements CogVideoX's v_prediction update only")
+        prev = timestep - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[timestep]
+        a_prev = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        a_back = self.alphas_cumprod[timestep_back] if timestep_back is not None else None
+        lamb = ((a_t / (1 - a_t)) ** 0.5).log()
+        lamb_next = ((a_prev / (1 - a_prev)) ** 0.5).log()
+        h = lamb_next - lamb
+        mult1 = ((1 - a_prev) / (1 - a_t)) ** 0.5 * (-h).exp()
+        mult2 = (-2 * h).expm1() * a_prev**0.5
+        m2 = m3 = None
+        if a_back is not None:
+            lamb_previous = ((a_back / (1 - a_back)) ** 0.5).log()
+            r = (lamb - lamb_previous) / h
+            m2, m3 = 1 + 1 / (2 * r), 1 / (2 * r)
+        mult_noise = (1 - a_prev) ** 0.5 * (1 - (-2 * h).exp()) ** 0.5
+
+        def on_bf16(c):   # multiplies a bf16 tensor
+            c = torch.as_tensor(c, dtype=torch.float64)
+            return float(c.to(torch.bfloat16)) if self.scalar_semantics == "cpu" else float(c.to(torch.float32))
+
+        def on_f32(c):
+            return float(torch.as_tensor(c, dtype=torch.float64).to(torch.float32))
+
+        second = a_back is not None and prev >= 0
+        return (on_bf16(a_t**0.5), on_f32((1 - a_t) ** 0.5), on_bf16(mult1), on_f32(mult2), on_f32(m2) if second else 1.0,
+                on_f32(m3) if second else 0.0, on_bf16(mult_noise), second)
+
+    @staticmethod
+    def _draw(sample: torch.Tensor, generator, variance_noise=None) -> torch.Tensor:
+        """randn_tensor(sample.shape, generator, device, dtype) (D/utils/torch_utils.py:38-83): drawn on the generator's device."""
+        if variance_noise is not None:
+            return variance_noise.to(device=sample.device, dtype=sample.dtype).contiguous()
+        gdev = generator.device if generator is not None else sample.device
+        return torch.randn(sample.shape, generator=generator, device=gdev, dtype=sample.dtype).to(sample.device).contiguous()
+
+    def _run(self, model_output, cfg_input, old_x0, timestep, timestep_back, sample, guidance, generator, variance_noise, prev_out):
+        t = self._as_int(timestep)
+        tb = None if timestep_back is None else self._as_int(timestep_back)
+        sa, sb, m0, m1, m2, m3, mn, second = self.dpm_coefficients(t, tb)
+        sample = sample.contiguous()
+        noise = self._draw(sample, generator, variance_noise)
+        use_old = second and old_x0 is not None
+        if use_old:
+            noise = self._draw(sample, generator, None)   # the reference draws again and uses the second draw (:432)
+        x0 = torch.empty(sample.shape, device=sample.device, dtype=torch.float32)
+        lib = _lib_mod.load()
+        _lib_mod.check(lib.s2v_dpm_step(model_output.data_ptr(), int(cfg_input), sample.data_ptr(),
+                                        old_x0.contiguous().data_ptr() if use_old else None, noise.data_ptr(), prev_out.data_ptr(),
+                                        x0.data_ptr(), sample.numel(), float(guidance), sa, sb, m0, m1, m2, m3, mn,
+                                        torch.cuda.current_stream().cuda_stream), "s2v_dpm_step")
+        return prev_out, x0
+
+    def step(self, model_output: torch.Tensor, old_pred_original_sample: Optional[torch.Tensor], timestep, timestep_back, sample: torch.Tensor,
+             eta: float = 0.0, use_clipped_model_output: bool = False, generator=None, variance_noise: Optional[torch.Tensor] = None,
+             return_dict: bool = False):
+        """Reference signature (:330-341): fp32 model_output, bf16 sample -> (fp32 prev_sample, fp32 pred_original_sample)."""
+        if sample.dtype != torch.bfloat16 or not sample.is_cuda:
+            raise RuntimeError("CogVideoXDPMScheduler.step: expected a CUDA bfloat16 sample")
+        mo = model_output.float().contiguous()
+        prev = torch.empty_like(mo)
+        prev, x0 = self._run(mo, 0, old_pred_original_sample, timestep, timestep_back, sample, 1.0, generator, variance_noise, prev)
+        if not return_dict:
+            return (prev, x0)
+        return DDIMSchedulerOutput(prev_sample=prev, pred_original_sample=x0)
+
+    def step_cfg_dpm(self, noise_pred: torch.Tensor, old_pred_original_sample, timestep, timestep_back, latents: torch.Tensor, guidance: float,
+                     generator=None, out: Optional[torch.Tensor] = None):
+        """Fused `.float()` -> CFG -> step -> `.to(bf16)`: noise_pred [2P, ...] bf16 (uncond first) -> (next latents bf16, x0 fp32)."""
+        out = torch.empty_like(latents) if out is None else out
+        return self._run(noise_pred.contiguous(), 1, old_pred_original_sample, timestep, timestep_back, latents, guidance, generator, None, out)

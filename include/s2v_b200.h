@@ -169,6 +169,18 @@ S2V_API int s2v_cfg_ddim_step(const void* noise_pred, const void* latents, void*
 S2V_API int s2v_ddim_step(const float* model_output, const void* sample, float* prev_out, float* x0_out, int64_t n,
                           float sqrt_alpha, float sqrt_beta, float a_coef, float b_coef, void* stream);
 
+/* DPM-Solver++ SDE multistep update (the `CogVideoXDPMScheduler` branch of the loop, S/custom_cogvideox_pipe.py:288-295;
+ * D/schedulers/scheduling_dpm_cogvideox.py:383-439), bit-exact with torch on CUDA:
+ *   x0 = bf16(sa*x) - sb*v;  d = old_x0 ? m2*x0 - m3*old_x0 : x0;  prev = (bf16(m0*x) - m1*d) + bf16(m_noise*noise)
+ * cfg_input = 1: model_output is the bf16 [2, n] CFG pair (uncond first), v = u + g*(t-u), prev_out is bf16 (the pipe's cast);
+ * cfg_input = 0: model_output is fp32 [n], prev_out fp32 (scheduler.step surface).  noise is the bf16 randn draw the caller
+ * made with the reference's generator protocol (two draws per second-order step; the second is the one used).  The host
+ * computes the seven coefficients in fp64 exactly as get_variables / get_mult (:306-328).  x0_out fp32 is mandatory (it is
+ * the next step's old_pred_original_sample). */
+S2V_API int s2v_dpm_step(const void* model_output, int32_t cfg_input, const void* sample, const float* old_x0, const void* noise,
+                         void* prev_out, float* x0_out, int64_t n, float guidance, float sqrt_alpha, float sqrt_beta, float m0, float m1,
+                         float m2, float m3, float m_noise, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ VAE decoder (row V)
  * Activations of the 3D causal VAE decoder live in padded channels-last VOLUMES  [t_pad + T, Hp, Wp, C]  bf16 with
  * Hp = H + 2, Wp = W + 2 (one zero pixel all round) and t_pad = 2 leading frames that hold the temporal context of a

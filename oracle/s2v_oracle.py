@@ -384,6 +384,33 @@ def ddim_step(ac: np.ndarray, model_output: torch.Tensor, t: int, sample: torch.
     return a * sample + b * x0, x0
 
 
+def dpm_step(ac: np.ndarray, model_output: torch.Tensor, old_x0: Optional[torch.Tensor], t: int, t_back: Optional[int],
+             sample: torch.Tensor, num_inference_steps: int, generator=None, num_train_timesteps: int = 1000):
+    """CogVideoXDPMScheduler.step (D/schedulers/scheduling_dpm_cogvideox.py:383-439; get_variables :306-317, get_mult :319-328),
+    v-prediction, with 0-dim fp64 coefficient tensors like the reference.  Draws noise with the reference's protocol
+    (one bf16/fp32 randn per call, a second one on second-order steps).  Returns (prev_sample, pred_original_sample)."""
+    act = torch.from_numpy(np.asarray(ac, dtype=np.float64))
+    prev_t = t - num_train_timesteps // num_inference_steps
+    a_t = act[t]
+    a_prev = act[prev_t] if prev_t >= 0 else torch.tensor(1.0)
+    a_back = act[t_back] if t_back is not None else None
+    x0 = (a_t**0.5) * sample - ((1 - a_t) ** 0.5) * model_output
+    lamb = ((a_t / (1 - a_t)) ** 0.5).log()
+    lamb_next = ((a_prev / (1 - a_prev)) ** 0.5).log()
+    h = lamb_next - lamb
+    mult1 = ((1 - a_prev) / (1 - a_t)) ** 0.5 * (-h).exp()
+    mult2 = (-2 * h).expm1() * a_prev**0.5
+    mult_noise = (1 - a_prev) ** 0.5 * (1 - (-2 * h).exp()) ** 0.5
+    noise = torch.randn(sample.shape, generator=generator, dtype=sample.dtype)
+    prev = mult1 * sample - mult2 * x0 + mult_noise * noise
+    if old_x0 is None or prev_t < 0:
+        return prev, x0
+    r = (lamb - ((a_back / (1 - a_back)) ** 0.5).log()) / h
+    d = (1 + 1 / (2 * r)) * x0 - (1 / (2 * r)) * old_x0
+    noise = torch.randn(sample.shape, generator=generator, dtype=sample.dtype)
+    return mult1 * sample - mult2 * d + mult_noise * noise, x0
+
+
 def cfg_combine(noise_pred: torch.Tensor, guidance: float) -> torch.Tensor:
     """S/custom_cogvideox_pipe.py:266,277-279: fp32, uncond first."""
     u, t = noise_pred.float().chunk(2)

@@ -240,6 +240,38 @@ def gen_pipe_loop():
     torch.save(fix, os.path.join(HERE, "pipe_loop_tiny.pt"))
 
 
+# ------------------------------------------------------------------ H. DPM scheduler trace (SURVEY §8f "next")
+def gen_dpm():
+    """50-step trace of the reference CogVideoXDPMScheduler on the CPU (bf16 sample, fp32 model output, seeded CPU generator),
+    with the loop protocol of S/custom_cogvideox_pipe.py:288-296 (old_pred_original_sample, timesteps[i-1], .to(bf16))."""
+    from diffusers.schedulers.scheduling_dpm_cogvideox import CogVideoXDPMScheduler
+
+    out = {}
+    for tag, snr in (("5b", 1.0), ("2b", 3.0)):
+        s = CogVideoXDPMScheduler(snr_shift_scale=snr, beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085,
+                                  clip_sample=False, num_train_timesteps=1000, prediction_type="v_prediction",
+                                  rescale_betas_zero_snr=True, set_alpha_to_one=True, timestep_spacing="trailing")
+        s.set_timesteps(50)
+        g = torch.Generator().manual_seed(4321)
+        gn = torch.Generator().manual_seed(99)
+        sample = torch.randn(1, 2, 16, 4, 6, generator=g).to(torch.bfloat16)
+        out[f"dpm_{tag}_sample0"] = sample.float().numpy()
+        old = None
+        prevs, x0s, mos = [], [], []
+        ts = s.timesteps
+        for i, t in enumerate(ts):
+            mo = torch.randn(sample.shape, generator=g, dtype=torch.float32)
+            prev, old = s.step(mo, old, t, ts[i - 1] if i > 0 else None, sample, generator=gn, return_dict=False)
+            assert prev.dtype == torch.float32 and old.dtype == torch.float32
+            mos.append(mo.numpy()); prevs.append(prev.numpy()); x0s.append(old.numpy())
+            sample = prev.to(torch.bfloat16)
+        out[f"dpm_{tag}_model_out"] = np.stack(mos)
+        out[f"dpm_{tag}_prev"] = np.stack(prevs)
+        out[f"dpm_{tag}_x0"] = np.stack(x0s)
+    np.savez_compressed(os.path.join(HERE, "scheduler_dpm.npz"), **out)
+    print("scheduler_dpm.npz", float(np.abs(out["dpm_5b_prev"][-1]).mean()))
+
+
 # ------------------------------------------------------------------ G. VAE decoder (row V)
 def gen_vae():
     """The reference AutoencoderKLCogVideoX (decoder half) with seeded weights: one decoder call with a conv-cache chain,
@@ -278,10 +310,11 @@ def gen_vae():
 
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["sched", "rope", "block", "transformer", "pipe", "vae"]
+    which = sys.argv[1:] or ["sched", "rope", "block", "transformer", "pipe", "vae", "dpm"]
     if "sched" in which: gen_scheduler()
     if "rope" in which: gen_rope()
     if "block" in which: gen_block()
     if "transformer" in which: gen_transformer()
     if "pipe" in which: gen_pipe_loop()
     if "vae" in which: gen_vae()
+    if "dpm" in which: gen_dpm()

@@ -357,3 +357,67 @@ def test_attention_v4_variant_matches_default(dev):
         ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
         err = float((out.float() - ref).abs().max() / ref.abs().max())
         assert err < 2e-2, (B, S, H, boost, err)
+
+
+# ---------------------------------------------------------------------------------------------- DPM scheduler (§8f next row)
+@pytest.mark.gpu
+def test_dpm_kernel_bit_exact_vs_cpu_reference_trace(dev, golden_dir):
+    """scalar_semantics='cpu': the fused DPM kernel + the reference's noise-draw protocol reproduce the reference
+    CogVideoXDPMScheduler's 50-step CPU trace bit for bit."""
+    import s2v_b200
+    g = np.load(os.path.join(golden_dir, "scheduler_dpm.npz"))
+    for tag, snr in (("5b", 1.0), ("2b", 3.0)):
+        s = s2v_b200.CogVideoXDPMScheduler.for_cogvideox(snr)
+        s.scalar_semantics = "cpu"
+        s.set_timesteps(50)
+        gn = torch.Generator().manual_seed(99)
+        x = torch.from_numpy(g[f"dpm_{tag}_sample0"]).to(BF16).to(dev)
+        old = None
+        ts = s._timesteps_host
+        for i, t in enumerate(ts):
+            v = torch.from_numpy(g[f"dpm_{tag}_model_out"][i]).to(dev)
+            prev, old = s.step(v, old, t, ts[i - 1] if i > 0 else None, x, generator=gn, return_dict=False)
+            assert np.array_equal(prev.cpu().numpy(), g[f"dpm_{tag}_prev"][i]), (tag, i)
+            assert np.array_equal(old.cpu().numpy(), g[f"dpm_{tag}_x0"][i]), (tag, i)
+            x = prev.to(BF16)
+
+
+@pytest.mark.gpu
+def test_dpm_cfg_kernel_bit_exact_vs_torch_cuda(dev):
+    """Default (CUDA) scalar semantics: identical to the reference's expressions evaluated by torch on the GPU with fp64 0-dim
+    CPU coefficient tensors, including CFG and the final .to(bf16), first- and second-order steps."""
+    import s2v_b200
+    s = s2v_b200.CogVideoXDPMScheduler.for_cogvideox(1.0)
+    s.set_timesteps(50)
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    lat = torch.randn(1, 13, 16, 60, 90, generator=gen).to(BF16).to(dev)
+    old = None
+    ts = s._timesteps_host
+    for i in (0, 1, 2, 30, 49):
+        t, tb = ts[i], (ts[i - 1] if i > 0 else None)
+        noise_pred = torch.randn(2, 13, 16, 60, 90, generator=gen).to(BF16).to(dev)
+        g1, g2 = torch.Generator(device=dev).manual_seed(11 + i), torch.Generator(device=dev).manual_seed(11 + i)
+        old_in = None if i == 0 else torch.randn(lat.shape, generator=gen).to(dev)
+        got, x0_got = s.step_cfg_dpm(noise_pred, old_in, t, tb, lat, 6.0, generator=g1)
+        # reference expressions on CUDA
+        u, c = noise_pred.float().chunk(2)
+        v = u + 6.0 * (c - u)
+        prev_t = t - 1000 // 50
+        a_t = s.alphas_cumprod[t]
+        a_prev = s.alphas_cumprod[prev_t] if prev_t >= 0 else s.final_alpha_cumprod
+        a_back = s.alphas_cumprod[tb] if tb is not None else None
+        x0 = (a_t**0.5) * lat - ((1 - a_t) ** 0.5) * v
+        lamb = ((a_t / (1 - a_t)) ** 0.5).log()
+        h = ((a_prev / (1 - a_prev)) ** 0.5).log() - lamb
+        m1 = ((1 - a_prev) / (1 - a_t)) ** 0.5 * (-h).exp()
+        m2 = (-2 * h).expm1() * a_prev**0.5
+        mn = (1 - a_prev) ** 0.5 * (1 - (-2 * h).exp()) ** 0.5
+        noise = torch.randn(lat.shape, generator=g2, device=dev, dtype=BF16)
+        want = m1 * lat - m2 * x0 + mn * noise
+        if old_in is not None and prev_t >= 0:
+            r = (lamb - ((a_back / (1 - a_back)) ** 0.5).log()) / h
+            d = (1 + 1 / (2 * r)) * x0 - (1 / (2 * r)) * old_in
+            noise = torch.randn(lat.shape, generator=g2, device=dev, dtype=BF16)
+            want = m1 * lat - m2 * d + mn * noise
+        assert torch.equal(x0_got, x0), i
+        assert torch.equal(got, want.to(BF16)), i

@@ -157,3 +157,20 @@ def test_pipe_loop_bf16_reference_noise_floor(golden_dir):
     fx = torch.load(os.path.join(golden_dir, "pipe_loop_tiny.pt"))
     d = (fx["runs"]["bf16"] - fx["runs"]["fp32"]).abs()
     assert 1e-4 < float(d.max()) < 0.2
+
+
+@pytest.mark.parametrize("tag,snr", [("5b", 1.0), ("2b", 3.0)])
+def test_dpm_step_trace_bit_exact(golden_dir, tag, snr):
+    """oracle dpm_step == the reference CogVideoXDPMScheduler CPU trace (incl. its two-draw noise protocol), bit for bit."""
+    g = np.load(os.path.join(golden_dir, "scheduler_dpm.npz"))
+    ac = O.ddim_alphas_cumprod(snr_shift_scale=snr)
+    ts = O.ddim_timesteps(50)
+    gn = torch.Generator().manual_seed(99)
+    sample = torch.from_numpy(g[f"dpm_{tag}_sample0"]).to(torch.bfloat16)
+    old = None
+    for i, t in enumerate(ts):
+        mo = torch.from_numpy(g[f"dpm_{tag}_model_out"][i])
+        prev, old = O.dpm_step(ac, mo, old, int(t), int(ts[i - 1]) if i > 0 else None, sample, 50, generator=gn)
+        assert np.array_equal(prev.numpy(), g[f"dpm_{tag}_prev"][i]), (tag, i)
+        assert np.array_equal(old.numpy(), g[f"dpm_{tag}_x0"][i]), (tag, i)
+        sample = prev.to(torch.bfloat16)
