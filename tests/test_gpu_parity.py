@@ -421,3 +421,39 @@ def test_dpm_cfg_kernel_bit_exact_vs_torch_cuda(dev):
             want = m1 * lat - m2 * d + mn * noise
         assert torch.equal(x0_got, x0), i
         assert torch.equal(got, want.to(BF16)), i
+
+
+# ---------------------------------------------------------------------------------------------- attach() on a foreign module tree
+@pytest.mark.gpu
+def test_attach_reads_peft_layout_of_an_already_built_model(dev, golden_dir):
+    """The S/inference.py route: a model tree that is NOT wired to the engine (its forward is a stub here, the stock diffusers
+    forward there) with LoRA injected by a PEFT-layout wrapper this package did not create (tests/golden/_peft_like.py:
+    base_layer / lora_A['default'] / lora_B['default'] / scaling['default']); `attach` must read the parameters in place and
+    reproduce the reference golden."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    import _peft_like
+    import s2v_b200
+    O = _O()
+    fx = torch.load(os.path.join(golden_dir, "transformer_tiny.pt"))["lora_rope"]
+    cfg = O.TransformerConfig(**fx["cfg"])
+    p16 = bf16_params(O.synth_params(cfg, seed=fx["seed"]))
+    m = s2v_b200.CogVideoXTransformer3DModel(num_attention_heads=cfg.num_attention_heads, num_layers=cfg.num_layers,
+                                             time_embed_dim=cfg.time_embed_dim, text_embed_dim=cfg.text_embed_dim,
+                                             use_rotary_positional_embeddings=True).to(BF16)
+    _peft_like.inject(m, cfg.lora_rank, cfg.lora_alpha)
+    _peft_like.load_flat_params(m, p16)
+
+    def stock_forward(*a, **k):
+        raise AssertionError("the stock forward must have been replaced by attach()")
+    m.forward = stock_forward
+    m = m.to(dev)
+    keys_before = set(m.state_dict().keys())
+    s2v_b200.attach(m)
+    assert set(m.state_dict().keys()) == keys_before                       # state-dict schema untouched
+    io = fx["io"]
+    rv, rr = O.pipeline_rope_tables(io["hidden"].shape[3] * 8, io["hidden"].shape[4] * 8, io["hidden"].shape[1])
+    got = m(io["hidden"].to(BF16).to(dev), io["ref"].to(BF16).to(dev), io["text"].to(BF16).to(dev), io["timestep"].to(dev),
+            image_rotary_emb=rv, ref_image_rotary_emb=rr, return_dict=False, eval=True)[0]
+    e_gold, _ = rel_err(got, fx["out"])
+    assert e_gold <= 3e-2, e_gold

@@ -258,3 +258,35 @@ def test_full_size_decode_is_deterministic_and_tile_consistent(dev):
     vae.disable_tiling()
     tile = vae.decode(z[:, :, :, :30, :45].contiguous()).sample                         # the first 30x45 latent tile alone
     assert torch.equal(a[:, :, :, :200, :288], tile[:, :, :, :200, :288])               # un-blended part of tile (0, 0)
+
+
+def test_attach_vae_on_a_stock_like_object(dev, fix, vae):
+    """attach_vae binds the engine to an object that only has the stock AutoencoderKLCogVideoX attributes (decoder tree,
+    dict-like config, tiling fields): same result as this package's class, bit for bit."""
+    import torch.nn as nn
+
+    import s2v_b200
+    from s2v_b200.vae import CogVideoXDecoder3D, _init_tiling
+    m, cfg, p = vae
+
+    class StockLike(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.config = dict(block_out_channels=cfg.block_out_channels, layers_per_block=cfg.layers_per_block, norm_num_groups=32,
+                               temporal_compression_ratio=4, latent_channels=16, scaling_factor=cfg.scaling_factor)
+            self.encoder = nn.Linear(4, 4)        # ignored: only decoder.* keys are read
+            self.decoder = CogVideoXDecoder3D(16, 3, cfg.block_out_channels, cfg.layers_per_block, 32, 4)
+            self.post_quant_conv = None
+            _init_tiling(self, cfg.sample_height, cfg.sample_width, len(cfg.block_out_channels))
+
+        def decode(self, z, return_dict=True):
+            raise AssertionError("stock decode must have been replaced")
+
+    s = StockLike()
+    s.load_state_dict({k: v for k, v in p.items()}, strict=False)
+    s = s.to(torch.bfloat16).to(dev)
+    s.use_tiling, s.use_slicing = True, True
+    s2v_b200.attach_vae(s)
+    m.enable_tiling(); m.enable_slicing()
+    z = fix["z"].to(torch.bfloat16).to(dev)
+    assert torch.equal(s.decode(z).sample, m.decode(z).sample)
