@@ -44,7 +44,20 @@ def v4(poly=1, skew=200):
     _lib.check(lib.s2v_attn_fwd_v4(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, poly, skew, torch.cuda.current_stream().cuda_stream), "v4")
 
 
-if hasattr(lib, "s2v_attn_fwd_v4"):
+def v1():
+    _lib.check(lib.s2v_attn_fwd_v1(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, torch.cuda.current_stream().cuda_stream), "v1")
+
+
+if hasattr(lib, "s2v_attn_fwd_v1") and "v1" in os.environ.get("S2V_SWEEP", "v1"):
+    lib.s2v_attn_set_poly16(1); lib.s2v_attn_set_skew_ns(200)
+    ops.attention(qkv, out, H); o_main = out.clone(); v1(); torch.cuda.synchronize()
+    print(json.dumps({"v1_max_abs_diff_vs_main": float((out.float() - o_main.float()).abs().max())}))
+    a, b = [], []
+    for rep in range(4):
+        a.append(timed(lambda: ops.attention(qkv, out, H)))
+        b.append(timed(v1))
+    print(json.dumps({"main_ms": [round(x, 3) for x in a], "v1_elect_ms": [round(x, 3) for x in b]}))
+if hasattr(lib, "s2v_attn_fwd_v4") and "v4" in os.environ.get("S2V_SWEEP", ""):
     lib.s2v_attn_set_poly16(1); lib.s2v_attn_set_skew_ns(200)
     ops.attention(qkv, out, H); o_main = out.clone(); v4(); torch.cuda.synchronize()
     print(json.dumps({"v4_max_abs_diff_vs_main": float((out.float() - o_main.float()).abs().max())}))
