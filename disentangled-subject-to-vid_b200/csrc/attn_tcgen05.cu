@@ -15,7 +15,7 @@
 // consumed.  Here S is double buffered and issued ONE TILE AHEAD of the PV product, so the softmax warps (the
 // MUFU-bound resource at head_dim 64: 16 ex2/clk/SM vs 8192 MMA flop/clk/SM) never wait for the tensor pipe:
 //
-//   tensor queue:   S0(t+1) S1(t+1) | PV0(t) PV1(t) | S0(t+2) S1(t+2) | PV0(t+1) ...
+//   per query tile q:   ... PV_q(t) S_q(t+2) | PV_q(t+1) S_q(t+3) ...     (the two q chains interleave as their P's arrive)
 //
 // Softmax (exp2 domain, FA-style online form) with three throughput measures, each taken from
 // tools/microbench_softmax.cu on B200 (profiles/r01_microbench.md):
@@ -185,46 +185,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
             // active and feeds tcgen05.mma's uniform-register operands directly; under `if (lane == 0)` it wrapped every
             // MMA in a warp-uniformisation loop (~80 issue cycles per MMA, which made the issuer the bottleneck).
             if (elect_one()) {
+                // ---- decoupled issue: each query tile has its own chain.  When P_q(t) is ready: PV_q(t), then
+                // S_q(t+2) straight into the buffer PV_q(t) has just consumed (in-order tensor pipe).  S_q(t+1) was issued
+                // when q finished tile t-1, so every warpgroup has a full tile of slack that does not depend on the other one.
+                int kv_waited = 0;
+                auto need_kv = [&](int t) {
+                    while (kv_waited <= t) {
+                        mbar_wait(&kv_full[kv_waited % ATT_STAGES], (kv_waited / ATT_STAGES) & 1);
+                        ++kv_waited;
+                    }
+                    tc_fence_after();
+                };
                 mbar_wait(q_ready, 0);
-                mbar_wait(&kv_full[0], 0);
                 tc_fence_after();
-                issue_s(0, 0, 0);
-                umma_commit(&s_full[0]);
-                issue_s(1, 0, 0);
-                umma_commit(&s_full[2]);
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int t = 0; t < n_kv; ++t) {
-                    int nstage = stage + 1;
-                    uint32_t nphase = phase;
-                    if (nstage == ATT_STAGES) {
-                        nstage = 0;
-                        nphase ^= 1;
-                    }
-                    // ---- scores of tile t+1 for both query tiles (their TMEM buffers were drained before p_ready(t-1))
-                    if (t + 1 < n_kv) {
-                        mbar_wait(&kv_full[nstage], nphase);
-                        tc_fence_after();
-                        const int nb = (t + 1) & 1;
-                        issue_s(0, nstage, nb);
-                        umma_commit(&s_full[nb]);
-                        issue_s(1, nstage, nb);
-                        umma_commit(&s_full[2 + nb]);
-                    }
-                    // ---- O_q += P_q(t) V(t)
-                    mbar_wait(&p_ready[t & 1], (t >> 1) & 1);
-                    tc_fence_after();
-                    issue_pv(0, stage, t != 0, t);
-                    umma_commit(&p_free[0]);
-                    mbar_wait(&p_ready[2 + (t & 1)], (t >> 1) & 1);
-                    tc_fence_after();
-                    issue_pv(1, stage, t != 0, t);
-                    umma_commit(&p_free[1]);
-                    umma_commit(&kv_empty[stage]);  // every MMA reading K(t)/V(t) has been issued before this point
-                    if (t + 1 == n_kv) umma_commit(o_final);
-                    stage = nstage;
-                    phase = nphase;
+                for (int t = 0; t < 2 && t < n_kv; ++t) {
+                    need_kv(t);
+                    issue_s(0, t % ATT_STAGES, t & 1);
+                    umma_commit(&s_full[t & 1]);
+                    issue_s(1, t % ATT_STAGES, t & 1);
+                    umma_commit(&s_full[2 + (t & 1)]);
                 }
+                int tq[2] = {0, 0};
+                while (tq[0] < n_kv || tq[1] < n_kv) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int t = tq[q];
+                        if (t < n_kv && mbar_test_wait(&p_ready[q * 2 + (t & 1)], (t >> 1) & 1)) {
+                            tc_fence_after();
+                            issue_pv(q, t % ATT_STAGES, t != 0, t);
+                            umma_commit(&p_free[q]);
+                            if (t + 2 < n_kv) {
+                                need_kv(t + 2);
+                                issue_s(q, (t + 2) % ATT_STAGES, t & 1);
+                                umma_commit(&s_full[q * 2 + (t & 1)]);
+                            }
+                            tq[q] = t + 1;
+                            if (tq[q ^ 1] > t) umma_commit(&kv_empty[t % ATT_STAGES]);   // both PV(t) issued: K(t)/V(t) may be refilled
+                        }
+                    }
+                }
+                umma_commit(o_final);
             }
             __syncwarp();
         }

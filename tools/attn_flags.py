@@ -14,7 +14,7 @@ def timed(iters=4):
     for _ in range(iters): ops.attention(qkv, out, H)
     e1.record(); torch.cuda.synchronize()
     return round(e0.elapsed_time(e1) / iters, 3)
-cfgs = {"base": 200, "nomma": 200 | (1 << 30)}
+cfgs = {"base": 200, "decoupled": 200 | (1 << 26), "decoupled_noskew": (1 << 26)}
 res = {k: [] for k in cfgs}
 for rep in range(3):
     for k, v in cfgs.items():
