@@ -99,8 +99,13 @@ __device__ __forceinline__ void exp2_poly2(uint64_t X, float& r0, float& r1, flo
 template <int POLY16>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H,
-                float scale_log2, int skew_ns) {
+                float scale_log2, int skew_ns, unsigned long long* __restrict__ dbg) {
     extern __shared__ uint8_t smem_raw[];
+    unsigned long long dbg_c0 = 0, dbg_t0 = 0;
+    if (dbg && threadIdx.x == 0) {
+        dbg_c0 = clock64();
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_t0));
+    }
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;                                     // STAGES x 8 KB
     uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;         // STAGES x 8 KB
@@ -400,6 +405,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (dbg && threadIdx.x == 0) {   // profiling aid: per-CTA SM cycles and wall nanoseconds -> effective SM clock of this launch
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        atomicAdd(dbg, (unsigned long long)(clock64() - dbg_c0));
+        atomicAdd(dbg + 1, t1 - dbg_t0);
+    }
 }
 
 }  // namespace s2v
@@ -407,6 +418,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
 using namespace s2v;
 
 static int g_att_poly16 = ATT_POLY16_DEFAULT;
+static unsigned long long* g_att_dbg = nullptr;   // optional device buffer [2]: summed per-CTA cycles, nanoseconds
+
+extern "C" int s2v_attn_set_debug_counters(void* dev_u64x2) {
+    g_att_dbg = static_cast<unsigned long long*>(dev_u64x2);
+    return 0;
+}
+
 static int g_att_skew_ns = 200;   // measured +4 % on B200 (tools/attn_sweep.py 1:0 1:150 1:300 ...)
 
 extern "C" int s2v_attn_set_skew_ns(int32_t ns) {
@@ -435,7 +453,7 @@ extern "C" int s2v_attn_fwd(const void* qkv, void* o, int32_t B, int32_t S, int3
     const uint32_t box[4] = {ATT_D, 1, ATT_BK, 1};
     if ((rc = make_tmap_nd_bf16(&tm, qkv, 4, dims, strides, box))) return rc;
     const int poly16 = g_att_poly16;
-    using kern_t = void (*)(const CUtensorMap, const bf16*, bf16*, int, int, float, int);
+    using kern_t = void (*)(const CUtensorMap, const bf16*, bf16*, int, int, float, int, unsigned long long*);
     static const kern_t kerns[9] = {attn_fwd_kernel<0>, attn_fwd_kernel<1>, attn_fwd_kernel<2>, attn_fwd_kernel<3>, attn_fwd_kernel<4>,
                                     attn_fwd_kernel<5>, attn_fwd_kernel<6>, attn_fwd_kernel<7>, attn_fwd_kernel<8>};
     static bool attr_done = false;
@@ -448,6 +466,7 @@ extern "C" int s2v_attn_fwd(const void* qkv, void* o, int32_t B, int32_t S, int3
     }
     dim3 grid((S + ATT_BQ * ATT_QTILES - 1) / (ATT_BQ * ATT_QTILES), H, B);
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    kerns[poly16]<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm, static_cast<const bf16*>(qkv), static_cast<bf16*>(o), S, H, scale_log2, g_att_skew_ns);
+    kerns[poly16]<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm, static_cast<const bf16*>(qkv), static_cast<bf16*>(o), S, H, scale_log2, g_att_skew_ns,
+                                                          g_att_dbg);
     return check_launch("attn_fwd_kernel");
 }
