@@ -32,6 +32,17 @@ class LinearArgs(C.Structure):
     ]
 
 
+class QkNormArgs(C.Structure):
+    """s2v_qk_norm_args (include/s2v_b200.h)."""
+
+    _fields_ = [
+        ("nq_w", C.c_void_p), ("nq_b", C.c_void_p), ("nk_w", C.c_void_p), ("nk_b", C.c_void_p),
+        ("cos", C.c_void_p), ("sin", C.c_void_p),
+        ("S", C.c_int32), ("H", C.c_int32), ("text_len", C.c_int32),
+        ("eps", C.c_float),
+    ]
+
+
 class ConvArgs(C.Structure):
     """s2v_conv_args (include/s2v_b200.h)."""
 
@@ -54,6 +65,7 @@ SIGNATURES = {
     "s2v_device_check": [C.c_int],
     "s2v_linear": [C.POINTER(LinearArgs), _vp],
     "s2v_qkv_lora": [C.POINTER(LinearArgs), _vp],
+    "s2v_qkv_lora_norm_rope": [C.POINTER(LinearArgs), C.POINTER(QkNormArgs), _vp],
     "s2v_outproj_lora_gate_residual": [C.POINTER(LinearArgs), _vp],
     "s2v_ffn_up_gelu_lora": [C.POINTER(LinearArgs), _vp],
     "s2v_ffn_down_lora_gate_residual": [C.POINTER(LinearArgs), _vp],

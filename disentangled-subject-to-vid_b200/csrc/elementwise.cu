@@ -203,7 +203,7 @@ qk_norm_rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ nq_w, const
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float d = v[j] - mean;
-            sq += d * d;
+            sq = fmaf(d, d, sq);
         }
         sq += __shfl_xor_sync(0xffffffffu, sq, 1);
         sq += __shfl_xor_sync(0xffffffffu, sq, 2);
@@ -211,7 +211,7 @@ qk_norm_rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ nq_w, const
         const float rstd = rsqrtf(sq * (1.0f / 64.0f) + eps);
         const bool is_q = hv < H;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * (is_q ? wq[j] : wk[j]) + (is_q ? bq[j] : bk[j]);
+        for (int j = 0; j < 8; ++j) v[j] = fmaf((v[j] - mean) * rstd, is_q ? wq[j] : wk[j], is_q ? bq[j] : bk[j]);
         if (rope) {
             // the reference rounds the LayerNorm output to bf16 before the fp32 rotation (attention_processor.py:2060-2066)
 #pragma unroll
@@ -219,8 +219,9 @@ qk_norm_rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ nq_w, const
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
-                o[j] = v[j] * c[j] - v[j + 1] * sn[j];
-                o[j + 1] = v[j + 1] * c[j + 1] + v[j] * sn[j + 1];
+                // explicit FMAs: head_norm_rope in gemm_tcgen05.cu (the fused epilogue) must round identically
+                o[j] = fmaf(v[j], c[j], -(v[j + 1] * sn[j]));
+                o[j + 1] = fmaf(v[j + 1], c[j + 1], v[j] * sn[j + 1]);
             }
             *ptr = pack8(o);
         } else {

@@ -35,9 +35,66 @@ struct GemmKParams {
     int tap_off[27];
     const bf16* res;
     long long ldres;
+    // fused q/k LayerNorm + RoPE (S2V_EPI_QKV_NORM_ROPE): columns [0, qk_cols) are 64-wide q then k head vectors
+    const bf16 *nq_w, *nq_b, *nk_w, *nk_b;
+    const float *rope_cos, *rope_sin;
+    int qk_cols;    // 2*H*64
+    float qk_eps;
 };
 
 constexpr int S2V_EPI_CONV = 3;
+constexpr int S2V_EPI_QKV_NORM_ROPE = 4;
+
+// Per-head LayerNorm(64) + interleaved RoPE on one head vector held by ONE thread, with exactly the arithmetic (operation
+// order, explicit FMAs, bf16 rounding points) of qk_norm_rope_kernel in elementwise.cu, so that the fused epilogue and the
+// stand-alone kernel produce identical bits.  f[] enters as bf16(acc + bias) values.
+__device__ __forceinline__ void head_norm_rope(float (&f)[64], const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                               const float* __restrict__ cs, const float* __restrict__ sn, float eps) {
+    float g[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a += f[l * 8 + j];
+        g[l] = a;
+    }
+    // the stand-alone kernel combines its 8 lanes with an xor-shuffle tree (1, 2, 4)
+    const float mean = (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) * (1.0f / 64.0f);
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = f[l * 8 + j] - mean;
+            a = fmaf(d, d, a);
+        }
+        g[l] = a;
+    }
+    const float rstd = rsqrtf((((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) * (1.0f / 64.0f) + eps);
+#pragma unroll
+    for (int v8 = 0; v8 < 8; ++v8) {
+        const uint4 wu = __ldg(reinterpret_cast<const uint4*>(w) + v8), bu = __ldg(reinterpret_cast<const uint4*>(b) + v8);
+        const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[v8 * 8 + 2 * j] = fmaf((f[v8 * 8 + 2 * j] - mean) * rstd, bf16_lo(ww[j]), bf16_lo(bw[j]));
+            f[v8 * 8 + 2 * j + 1] = fmaf((f[v8 * 8 + 2 * j + 1] - mean) * rstd, bf16_hi(ww[j]), bf16_hi(bw[j]));
+        }
+    }
+    if (cs) {
+#pragma unroll
+        for (int v4 = 0; v4 < 16; ++v4) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs) + v4), s4 = __ldg(reinterpret_cast<const float4*>(sn) + v4);
+            const float c[4] = {c4.x, c4.y, c4.z, c4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+                const float x0 = __bfloat162float(__float2bfloat16(f[v4 * 4 + j])), x1 = __bfloat162float(__float2bfloat16(f[v4 * 4 + j + 1]));
+                f[v4 * 4 + j] = fmaf(x0, c[j], -(x1 * sv[j]));
+                f[v4 * 4 + j + 1] = fmaf(x1, c[j + 1], x0 * sv[j + 1]);
+            }
+        }
+    }
+}
 
 template <int BN>
 struct GemmCfg {
@@ -208,6 +265,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int s = row - b * p.rows_per_batch;
                 gate = p.mod + (long long)b * p.mod_stride + (s < p.text_len ? p.gate_off_text : p.gate_off_other) + n0;
             }
+            if (EPI == S2V_EPI_QKV_NORM_ROPE) {
+                // one 64-column head vector at a time (BN is a multiple of 64 and head boundaries are 64-aligned)
+                const int sidx = row_ok ? row % p.rows_per_batch : 0;
+                const bool rope = p.rope_cos != nullptr && sidx >= p.text_len;
+                const float* cs = rope ? p.rope_cos + (long long)(sidx - p.text_len) * 64 : nullptr;
+                const float* sn = rope ? p.rope_sin + (long long)(sidx - p.text_len) * 64 : nullptr;
+#pragma unroll 1
+                for (int hv = 0; hv < BN / 64; ++hv) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + hv * 64, v0);
+                    tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + hv * 64 + 32, v1);
+                    tmem_ld_wait();
+                    const int col0 = n0 + hv * 64;
+                    if (row_ok && col0 < p.N) {
+                        float f[64];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            f[j] = __uint_as_float(v0[j]) * p.alpha;
+                            f[32 + j] = __uint_as_float(v1[j]) * p.alpha;
+                        }
+                        if (p.bias) {
+#pragma unroll
+                            for (int v8 = 0; v8 < 8; ++v8) {
+                                const uint4 bb = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + v8);
+                                const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    f[v8 * 8 + 2 * j] += bf16_lo(bw[j]);
+                                    f[v8 * 8 + 2 * j + 1] += bf16_hi(bw[j]);
+                                }
+                            }
+                        }
+                        if (col0 < p.qk_cols) {
+#pragma unroll
+                            for (int j = 0; j < 64; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));   // the projection output is bf16
+                            const bool is_q = col0 < (p.qk_cols >> 1);
+                            head_norm_rope(f, is_q ? p.nq_w : p.nk_w, is_q ? p.nq_b : p.nk_b, cs, sn, p.qk_eps);
+                        }
+#pragma unroll
+                        for (int v8 = 0; v8 < 8; ++v8) {
+                            uint4 o;
+                            o.x = pack_bf16x2(f[v8 * 8 + 0], f[v8 * 8 + 1]);
+                            o.y = pack_bf16x2(f[v8 * 8 + 2], f[v8 * 8 + 3]);
+                            o.z = pack_bf16x2(f[v8 * 8 + 4], f[v8 * 8 + 5]);
+                            o.w = pack_bf16x2(f[v8 * 8 + 6], f[v8 * 8 + 7]);
+                            *reinterpret_cast<uint4*>(orow + hv * 64 + v8 * 8) = o;
+                        }
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
@@ -296,7 +403,7 @@ struct ConvExtra {
 };
 
 template <int BN, int EPI>
-static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const ConvExtra* conv = nullptr) {
+static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const ConvExtra* conv = nullptr, const s2v_qk_norm_args* qk = nullptr) {
     using Cfg = GemmCfg<BN>;
     CUtensorMap tmA, tmB, tmA2, tmB2;
     int rc;
@@ -323,6 +430,13 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
     p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->M; p.text_len = a->text_len;
     p.taps = 1; p.cin_blocks = (a->K + GEMM_BK - 1) / GEMM_BK; p.a_row0 = 0; p.out_row0 = 0; p.Hp = 1; p.Wp = 1;
     p.res = nullptr; p.ldres = 0;
+    p.nq_w = p.nq_b = p.nk_w = p.nk_b = nullptr; p.rope_cos = p.rope_sin = nullptr; p.qk_cols = 0; p.qk_eps = 0.f;
+    if (qk) {
+        p.nq_w = static_cast<const bf16*>(qk->nq_w); p.nq_b = static_cast<const bf16*>(qk->nq_b);
+        p.nk_w = static_cast<const bf16*>(qk->nk_w); p.nk_b = static_cast<const bf16*>(qk->nk_b);
+        p.rope_cos = qk->cos; p.rope_sin = qk->sin; p.qk_cols = 2 * qk->H * 64; p.qk_eps = qk->eps;
+        p.rows_per_batch = qk->S; p.text_len = qk->text_len;
+    }
     if (conv) {
         p.taps = conv->taps; p.cin_blocks = (conv->cin + GEMM_BK - 1) / GEMM_BK; p.a_row0 = conv->a_row0; p.out_row0 = conv->out_row0;
         p.Hp = conv->Hp; p.Wp = conv->Wp; p.res = static_cast<const bf16*>(conv->res); p.ldres = conv->ldres;
@@ -378,6 +492,25 @@ extern "C" int s2v_linear(const s2v_linear_args* a, void* stream_) {
 }
 
 extern "C" int s2v_qkv_lora(const s2v_linear_args* a, void* stream) { return s2v_linear(a, stream); }
+
+extern "C" int s2v_qkv_lora_norm_rope(const s2v_linear_args* a, const s2v_qk_norm_args* qk, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!a || !qk || !a->x || !a->w || !a->out || !qk->nq_w || !qk->nq_b || !qk->nk_w || !qk->nk_b)
+        return set_error(S2V_E_BADARG, "s2v_qkv_lora_norm_rope: null pointer");
+    if (a->M <= 0 || a->K <= 0 || qk->H <= 0 || qk->S <= 0 || a->N != 3 * qk->H * 64 || (a->M % qk->S))
+        return set_error(S2V_E_BADARG, "s2v_qkv_lora_norm_rope: expected N = 3*H*64 and M = B*S");
+    if ((a->K % 8) || (a->ldx % 8) || (a->ldw % 8) || (a->ldo % 8)) return set_error(S2V_E_UNSUPPORTED, "s2v_qkv_lora_norm_rope: K and leading dims must be multiples of 8");
+    if ((qk->cos == nullptr) != (qk->sin == nullptr)) return set_error(S2V_E_BADARG, "s2v_qkv_lora_norm_rope: cos and sin go together");
+    if (a->lora_t) {
+        if (!a->lora_b || a->lora_r <= 0 || (a->lora_r % 8) || (a->ldt % 8) || (a->ldb % 8) || (a->lora_group_n != qk->H * 64))
+            return set_error(S2V_E_BADARG, "s2v_qkv_lora_norm_rope: bad LoRA operands (one group per q, k, v)");
+    }
+    int rc = ensure_device();
+    if (rc) return rc;
+    const int gn = qk->H * 64;
+    const bool wide = (gn % 256 == 0) || !a->lora_t;
+    return wide ? launch_gemm<256, S2V_EPI_QKV_NORM_ROPE>(a, stream, nullptr, qk) : launch_gemm<128, S2V_EPI_QKV_NORM_ROPE>(a, stream, nullptr, qk);
+}
 extern "C" int s2v_outproj_lora_gate_residual(const s2v_linear_args* a, void* stream) {
     if (a && a->epilogue != S2V_EPI_GATE_RESIDUAL) return set_error(S2V_E_BADARG, "outproj: epilogue must be GATE_RESIDUAL");
     return s2v_linear(a, stream);

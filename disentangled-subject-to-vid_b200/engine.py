@@ -19,6 +19,7 @@ replacing the ~60 library kernels and 4 full-activation cat/split copies the ref
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -28,6 +29,9 @@ from . import ops
 from .lora import LinearParams, read_linear
 
 BF16 = torch.bfloat16
+# q/k LayerNorm + RoPE inside the QKV GEMM epilogue (s2v_qkv_lora_norm_rope); S2V_FUSED_QK_NORM=0 selects the two-kernel
+# form (s2v_qkv_lora + s2v_qk_norm_rope) for A/B runs — same kernels' arithmetic, identical bits
+FUSED_QK_NORM = os.environ.get("S2V_FUSED_QK_NORM", "1") != "0"
 
 
 @dataclass
@@ -171,9 +175,15 @@ class BlockRunner:
     def attention_core(self, pb: PackedBlock, ws: Workspace, x_in: torch.Tensor, rope: Optional[Tuple[torch.Tensor, torch.Tensor]]):
         """x_in [B,S,D] (normalised tokens) -> ws.att [B,S,D] = attention output BEFORE the out-projection."""
         B, S, D = x_in.shape
-        self.linear(pb.qkv, x_in.view(B * S, D), ws.qkv.view(B * S, 3 * D), ws, entry="s2v_qkv_lora")
         cos, sin = rope if rope is not None else (None, None)
-        ops.qk_norm_rope(ws.qkv, pb.nq_w, pb.nq_b, pb.nk_w, pb.nk_b, cos, sin, self.heads, self.text_len, pb.qk_eps)
+        if FUSED_QK_NORM:
+            # K1+K2+K3 in one launch: LayerNorm(64) + RoPE of the q/k heads in the projection's epilogue (bit-identical to
+            # the two-kernel form below, one read+write of 2/3 of qkv less)
+            qk = ops.qk_norm_args(pb.nq_w, pb.nq_b, pb.nk_w, pb.nk_b, cos, sin, S, self.heads, self.text_len, pb.qk_eps)
+            self.linear(pb.qkv, x_in.view(B * S, D), ws.qkv.view(B * S, 3 * D), ws, entry="s2v_qkv_lora", qk=qk)
+        else:
+            self.linear(pb.qkv, x_in.view(B * S, D), ws.qkv.view(B * S, 3 * D), ws, entry="s2v_qkv_lora")
+            ops.qk_norm_rope(ws.qkv, pb.nq_w, pb.nq_b, pb.nk_w, pb.nk_b, cos, sin, self.heads, self.text_len, pb.qk_eps)
         ops.attention(ws.qkv, ws.att, self.heads)
         return ws.att
 

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, LinearArgs  # noqa: F401
+from ._lib import EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, LinearArgs, QkNormArgs  # noqa: F401
 
 BF16 = torch.bfloat16
 
@@ -100,8 +100,9 @@ def _rows(t: torch.Tensor):
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, *, epilogue: int = EPI_BIAS,
            alpha: float = 1.0, lora_t: Optional[torch.Tensor] = None, lora_b: Optional[torch.Tensor] = None,
            lora_group_n: int = 0, mod: Optional[torch.Tensor] = None, gate_off_text: int = 0, gate_off_other: int = 0,
-           rows_per_batch: int = 0, text_len: int = 0, entry: str = "s2v_linear") -> torch.Tensor:
-    """out[M,N] = epilogue(alpha * x[M,K] @ w[N,K]^T (+ lora_t @ lora_b^T) + bias).  See s2v_linear."""
+           rows_per_batch: int = 0, text_len: int = 0, entry: str = "s2v_linear", qk: Optional[QkNormArgs] = None) -> torch.Tensor:
+    """out[M,N] = epilogue(alpha * x[M,K] @ w[N,K]^T (+ lora_t @ lora_b^T) + bias).  See s2v_linear.
+    With `qk` (built by qk_norm_args) the launch is s2v_qkv_lora_norm_rope: the q/k LayerNorm(64) + RoPE run in the epilogue."""
     for t, n in ((x, "x"), (w, "w"), (out, "out")):
         _chk_bf16(t, n)
     M, K, ldx = _rows(x)
@@ -138,8 +139,32 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: 
     a.gate_off_text, a.gate_off_other, a.rows_per_batch, a.text_len = gate_off_text, gate_off_other, rows_per_batch, text_len
     lib = _lib.load()
     with _timed(entry):
-        _lib.check(getattr(lib, entry)(C.byref(a), _stream()), entry)
+        if qk is not None:
+            _lib.check(lib.s2v_qkv_lora_norm_rope(C.byref(a), C.byref(qk), _stream()), "s2v_qkv_lora_norm_rope")
+        else:
+            _lib.check(getattr(lib, entry)(C.byref(a), _stream()), entry)
     return out
+
+
+def qk_norm_args(nq_w, nq_b, nk_w, nk_b, cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], S: int, heads: int,
+                 text_len: int, eps: float = 1e-6) -> QkNormArgs:
+    """Argument block of s2v_qkv_lora_norm_rope (the tensors must outlive the launch; the caller keeps them)."""
+    for t, n in ((nq_w, "nq_w"), (nq_b, "nq_b"), (nk_w, "nk_w"), (nk_b, "nk_b")):
+        _chk_bf16(t, n)
+        if t.numel() != 64 or not t.is_contiguous():
+            raise RuntimeError(f"qk_norm_args: {n} must be a contiguous [64] tensor")
+    if (cos is None) != (sin is None):
+        raise RuntimeError("qk_norm_args: cos and sin go together")
+    if cos is not None:
+        _chk_f32(cos, "cos"); _chk_f32(sin, "sin")
+        if tuple(cos.shape) != (S - text_len, 64) or tuple(sin.shape) != (S - text_len, 64) or not cos.is_contiguous() \
+                or not sin.is_contiguous():
+            raise RuntimeError(f"qk_norm_args: cos/sin must be contiguous [{S - text_len},64]")
+    q = QkNormArgs()
+    q.nq_w, q.nq_b, q.nk_w, q.nk_b = nq_w.data_ptr(), nq_b.data_ptr(), nk_w.data_ptr(), nk_b.data_ptr()
+    q.cos, q.sin = _ptr(cos), _ptr(sin)
+    q.S, q.H, q.text_len, q.eps = S, heads, text_len, eps
+    return q
 
 
 # which attention kernel `attention()` launches: "default" (8 softmax warps) or "v4" (16 softmax warps) — both are sm_100a

@@ -251,6 +251,16 @@ S2V_API int s2v_vae_blend(const void* a, void* b, int64_t n_outer, int32_t exten
 /* ------------------------------------------------------------------------------------------------ stage wrappers
  * Thin named entry points (the per-stage ABI proposed in SURVEY.md §8b); each forwards to s2v_linear. */
 S2V_API int s2v_qkv_lora(const s2v_linear_args* a, void* stream);                     /* K1: to_q|to_k|to_v + LoRA, bias      */
+/* K1 + K2 + K3 in one launch: the fused q|k|v projection (bias, LoRA) whose epilogue applies the per-head LayerNorm(64) and
+ * the interleaved RoPE of s2v_qk_norm_rope to the q and k head vectors before they are stored (bit-identical to running
+ * s2v_qkv_lora followed by s2v_qk_norm_rope; saves one read + write of 2/3 of qkv per block). */
+typedef struct {
+    const void *nq_w, *nq_b, *nk_w, *nk_b;   /* [64] bf16 each */
+    const float *cos, *sin;                  /* [S - text_len, 64] fp32 or both NULL */
+    int32_t S, H, text_len;
+    float eps;
+} s2v_qk_norm_args;
+S2V_API int s2v_qkv_lora_norm_rope(const s2v_linear_args* a, const s2v_qk_norm_args* qk, void* stream);
 S2V_API int s2v_outproj_lora_gate_residual(const s2v_linear_args* a, void* stream);   /* K5+K8                                */
 S2V_API int s2v_ffn_up_gelu_lora(const s2v_linear_args* a, void* stream);             /* K10 first half                       */
 S2V_API int s2v_ffn_down_lora_gate_residual(const s2v_linear_args* a, void* stream);  /* K10 second half + K8                 */

@@ -457,3 +457,38 @@ def test_attach_reads_peft_layout_of_an_already_built_model(dev, golden_dir):
             image_rotary_emb=rv, ref_image_rotary_emb=rr, return_dict=False, eval=True)[0]
     e_gold, _ = rel_err(got, fx["out"])
     assert e_gold <= 3e-2, e_gold
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,S,H,L,lora,rope", [(2, 300, 2, 226, True, True), (1, 1000, 4, 226, False, True),
+                                                (2, 517, 6, 226, True, False), (1, 19126, 48, 226, True, True)])
+def test_fused_qkv_norm_rope_is_bit_identical_to_the_two_kernel_form(dev, B, S, H, L, lora, rope):
+    """s2v_qkv_lora_norm_rope (LayerNorm(64)+RoPE in the GEMM epilogue) == s2v_qkv_lora followed by s2v_qk_norm_rope, bit for
+    bit (D/models/attention_processor.py:2046-2076): same bf16 rounding of the projection, same reduction tree, same FMAs."""
+    from s2v_b200 import ops
+    g = torch.Generator().manual_seed(100 + S)
+    D = H * 64
+    r = 16
+    x = torch.randn(B * S, D, generator=g).to(BF16).to(dev)
+    w = (torch.randn(3 * D, D, generator=g) * 0.05).to(BF16).to(dev)
+    b = (torch.randn(3 * D, generator=g) * 0.1).to(BF16).to(dev)
+    nq_w, nk_w = [(1 + 0.1 * torch.randn(64, generator=g)).to(BF16).to(dev) for _ in range(2)]
+    nq_b, nk_b = [(0.1 * torch.randn(64, generator=g)).to(BF16).to(dev) for _ in range(2)]
+    t = (torch.randn(B * S, 3 * r, generator=g) * 0.3).to(BF16).to(dev) if lora else None
+    lb = (torch.randn(3 * D, r, generator=g) * 0.05).to(BF16).to(dev) if lora else None
+    cos = sin = None
+    if rope:
+        ang = torch.rand(S - L, 32, generator=g) * 6.28
+        cos = torch.cos(ang).repeat_interleave(2, dim=1).contiguous().to(dev)
+        sin = torch.sin(ang).repeat_interleave(2, dim=1).contiguous().to(dev)
+    two = torch.empty(B, S, 3 * D, dtype=BF16, device=dev)
+    ops.linear(x, w, b, two.view(B * S, 3 * D), lora_t=t, lora_b=lb, lora_group_n=D, entry="s2v_qkv_lora")
+    plain = two.clone()
+    ops.qk_norm_rope(two, nq_w, nq_b, nk_w, nk_b, cos, sin, H, L)
+    one = torch.empty_like(two)
+    qk = ops.qk_norm_args(nq_w, nq_b, nk_w, nk_b, cos, sin, S, H, L)
+    ops.linear(x, w, b, one.view(B * S, 3 * D), lora_t=t, lora_b=lb, lora_group_n=D, entry="s2v_qkv_lora", qk=qk)
+    torch.cuda.synchronize()
+    assert torch.equal(one[..., 2 * D:], plain[..., 2 * D:])          # v columns untouched
+    assert not torch.equal(one[..., : 2 * D], plain[..., : 2 * D])    # q/k were transformed
+    assert torch.equal(one, two), f"max diff {(one.float() - two.float()).abs().max().item()}"
