@@ -52,7 +52,7 @@ for a in sys.argv[1:]:
 if not configs:
     configs = {"default_p1_s200": ("default", 1, 200), "default_p0_s200": ("default", 0, 200), "default_p2_s200": ("default", 2, 200),
                "default_p1_s0": ("default", 1, 0), "v4_p1_s0": ("v4", 1, 0)}
-dbg = torch.zeros(2, dtype=torch.int64, device=dev)
+dbg = torch.zeros(42, dtype=torch.int64, device=dev)
 lib.s2v_attn_set_debug_counters(dbg.data_ptr())
 run(2)  # warm up (clocks settle on the power cap)
 res = {k: [] for k in configs}
@@ -64,7 +64,7 @@ for rep in range(2):
         lib.s2v_attn_set_skew_ns(skew)
         dbg.zero_()
         r = run(2)
-        c, ns = [int(x) for x in dbg.tolist()]
+        c, ns = [int(x) for x in dbg.tolist()[:2]]
         res[k].append(r + (round(c / max(ns, 1) * 1e3), round(c / (2 * 42 * 7200) / 299)))   # + (attention SM MHz, cycles per 64-key step)
 for k, v in res.items():
     print(json.dumps({"config": k, "attn_ms, step_ms, attn_sm_mhz, cycles_per_step": v}))
@@ -79,5 +79,5 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record()
 for _ in range(20): ops.attention(qkv, out, w["heads"])
 e1.record(); torch.cuda.synchronize()
-c, ns = [int(x) for x in dbg.tolist()]
+c, ns = [int(x) for x in dbg.tolist()[:2]]
 print(json.dumps({"isolated_sustained_attn_ms": round(e0.elapsed_time(e1) / 20, 3), "attn_sm_mhz": round(c / ns * 1e3), "cycles_per_step": round(c / (20 * 7200) / 299)}))

@@ -72,6 +72,8 @@ void run(const char* name) {
 }
 
 int main() {
+    run<0, 4>("ex2 chain only");
+    run<7, 4>("ffma2 + ex2 + fadd2 + f2fp");
     run<0, 8>("ex2 chain only");
     run<0, 16>("ex2 chain only");
     run<1, 8>("ffma2 + ex2");
