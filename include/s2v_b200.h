@@ -92,12 +92,9 @@ S2V_API int s2v_attn_fwd(const void* qkv, void* o, int32_t B, int32_t S, int32_t
 /* Tuning knob (process-wide, not thread-safe): how many of every 8 exponential PAIRS the softmax evaluates with the FMA-pipe
  * polynomial instead of MUFU.EX2 (0..8).  Every setting computes the same function to within 7.5e-5 relative error. */
 S2V_API int s2v_attn_set_poly16(int32_t pairs_of_8);
-/* Profiling aid: when set to a device buffer of 42 uint64, every s2v_attn_fwd launch adds to it: [0] per-CTA SM cycles, [1]
- * per-CTA wall-clock nanoseconds (sum cycles / sum ns = the SM clock the kernel actually ran at), [2..9] cycles each softmax
- * warp slot (query tile * 4 + TMEM lane quarter) spent waiting for its score tile, [10..17] cycles the slot spent in its tile
- * loop, [18..23] per MMA-issuing thread (query tile 0, 1): cycles blocked on P, cycles issuing, cycles blocked on K/V; the rest
- * is reserved.  NULL (default) disables. */
-S2V_API int s2v_attn_set_debug_counters(void* dev_u64x42);
+/* Profiling aid: when set to a device buffer of two uint64, every s2v_attn_fwd launch adds its per-CTA SM cycle counts and
+ * wall-clock nanoseconds to it (sum cycles / sum ns = the SM clock the kernel actually ran at).  NULL (default) disables. */
+S2V_API int s2v_attn_set_debug_counters(void* dev_u64x2);
 /* Variant of s2v_attn_fwd with 16 softmax warps (two threads per query row); same contract and results to rounding.  Kept
  * beside the default for in-process A/B measurement (tools/attn_sweep.py); poly16 in 0..2. */
 S2V_API int s2v_attn_fwd_v4(const void* qkv, void* o, int32_t B, int32_t S, int32_t H, float softmax_scale, int32_t poly16,
