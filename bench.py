@@ -31,6 +31,8 @@ WORKLOADS = {
     "cfg3": dict(model="CogVideoX-5B", heads=48, layers=42, rotary=True, lora=(128, 64.0), frames=49, height=480, width=720, snr=1.0),
     # BASELINE.json configs[1]: CogVideoX-2B, 13 latent frames (49 px frames) 480x720, no LoRA
     "cfg2": dict(model="CogVideoX-2B", heads=30, layers=30, rotary=False, lora=None, frames=49, height=480, width=720, snr=3.0),
+    # BASELINE.json configs[3] geometry on one GPU: CogVideoX-5B + LoRA, 49 frames 720x1280 (S = 50 626), CFG batch 2
+    "cfg4": dict(model="CogVideoX-5B", heads=48, layers=42, rotary=True, lora=(128, 64.0), frames=49, height=720, width=1280, snr=1.0),
     # quick functional check (not a bench line)
     "tiny": dict(model="tiny", heads=2, layers=2, rotary=True, lora=(8, 4.0), frames=9, height=64, width=96, snr=1.0),
 }
