@@ -21,7 +21,7 @@ from .modules import (  # noqa: F401
     CogVideoXTransformer3DModel,
     attach,
 )
-from .pipeline import CogVideoXPipelineOutput, CustomCogVideoXPipeline  # noqa: F401
+from .pipeline import CogVideoXPipelineOutput, CustomCogVideoXPipeline, export_to_video, postprocess_video  # noqa: F401
 from .scheduler import CogVideoXDDIMScheduler, CogVideoXDPMScheduler  # noqa: F401
 from .vae import AutoencoderKLCogVideoX, attach_vae  # noqa: F401
 

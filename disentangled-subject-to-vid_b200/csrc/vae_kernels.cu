@@ -226,6 +226,45 @@ __global__ void volume_to_video_kernel(const bf16* __restrict__ vol, bf16* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------ video -> uint8 frames
+// The host glue after the decoder (D/video_processor.py:89-113 postprocess_video -> D/image_processor.py:227-239 denormalize,
+// :196-208 pt_to_numpy, :133-150 numpy_to_pil; D/utils/export_utils.py:177-178 export_to_video) done on the device, with the
+// reference's rounding points:  d = bf16(bf16(v / 2) + 0.5)  clamped to [0, 1]  (two bf16 tensor ops),  then in fp32
+// d * 255 -> uint8 by truncation (export_to_video's astype) or round-half-even (numpy_to_pil's .round()).
+// video [B, 3, F, H, W] bf16 -> frames [B, F, H, W, 3] uint8: 6 bytes read + 3 bytes written per pixel instead of a 4-byte
+// fp32 copy per channel to the host.  One thread = 4 consecutive pixels of one frame (8-byte loads per plane, 12-byte store).
+__device__ __forceinline__ uint32_t px_u8(float v, int round_mode) {
+    float d = bf16_round(bf16_round(v * 0.5f) + 0.5f);
+    d = fminf(fmaxf(d, 0.f), 1.f);
+    const float y = d * 255.0f;
+    return (uint32_t)(round_mode ? rintf(y) : floorf(y));
+}
+__global__ void __launch_bounds__(256)
+video_to_uint8_kernel(const bf16* __restrict__ video, uint8_t* __restrict__ out, int B, int F, long long HW, int round_mode) {
+    const long long groups = HW / 4;                       // 4-pixel groups per frame (host checks HW % 4 == 0)
+    const long long n = (long long)B * F * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long g = i % groups;
+        const long long bf = i / groups;
+        const int f = (int)(bf % F);
+        const int b = (int)(bf / F);
+        uint32_t px[12];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(video + (((long long)b * 3 + c) * F + f) * HW) + g);
+            px[0 * 3 + c] = px_u8(bf16_lo(u.x), round_mode);
+            px[1 * 3 + c] = px_u8(bf16_hi(u.x), round_mode);
+            px[2 * 3 + c] = px_u8(bf16_lo(u.y), round_mode);
+            px[3 * 3 + c] = px_u8(bf16_hi(u.y), round_mode);
+        }
+        uint32_t w[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = px[4 * k] | (px[4 * k + 1] << 8) | (px[4 * k + 2] << 16) | (px[4 * k + 3] << 24);
+        uint32_t* o = reinterpret_cast<uint32_t*>(out + ((long long)(b * F + f) * HW + g * 4) * 3);
+        o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ seam blending
 // b[o, y, x] = a[o, La - extent + y, x] * (1 - y/extent) + b[o, y, x] * (y/extent) for y < extent along the blended axis,
 // with torch's bf16 rounding points (each product and the sum are rounded): autoencoder_kl_cogvideox.py:1284-1298.
@@ -346,6 +385,23 @@ extern "C" int s2v_vae_volume_to_video(const void* vol, void* video, int32_t T, 
     volume_to_video_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(vol), static_cast<bf16*>(video),
                                                                                            T, H, W, ldc, Cout, Tv, f0);
     return check_launch("volume_to_video_kernel");
+}
+
+extern "C" int s2v_video_to_uint8(const void* video, void* frames, int32_t B, int32_t F, int32_t H, int32_t W, int32_t round_mode,
+                                  void* stream) {
+    if (!video || !frames) return set_error(S2V_E_BADARG, "s2v_video_to_uint8: null pointer");
+    if (B <= 0 || F <= 0 || H <= 0 || W <= 0) return set_error(S2V_E_BADARG, "s2v_video_to_uint8: empty video");
+    if (round_mode != 0 && round_mode != 1) return set_error(S2V_E_BADARG, "s2v_video_to_uint8: round_mode is 0 (truncate) or 1 (round half even)");
+    const long long HW = (long long)H * W;
+    if (HW % 4) return set_error(S2V_E_UNSUPPORTED, "s2v_video_to_uint8: H*W must be a multiple of 4");
+    if ((reinterpret_cast<uintptr_t>(video) & 7) || (reinterpret_cast<uintptr_t>(frames) & 3))
+        return set_error(S2V_E_BADARG, "s2v_video_to_uint8: video must be 8-byte and frames 4-byte aligned");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const long long n = (long long)B * F * (HW / 4);
+    video_to_uint8_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(video),
+                                                                                          static_cast<uint8_t*>(frames), B, F, HW, round_mode);
+    return check_launch("video_to_uint8_kernel");
 }
 
 extern "C" int s2v_vae_blend(const void* a, void* b, int64_t n_outer, int32_t extent, int32_t n_other, int32_t a_len, int64_t a_so,

@@ -328,3 +328,18 @@ def ddim_step(model_output: torch.Tensor, sample: torch.Tensor, prev_out: torch.
     _lib.check(lib.s2v_ddim_step(model_output.data_ptr(), sample.data_ptr(), prev_out.data_ptr(), _ptr(x0_out), n, sqrt_alpha,
                                  sqrt_beta, a_coef, b_coef, _stream()), "s2v_ddim_step")
     return prev_out
+
+
+def video_to_uint8(video: torch.Tensor, round_half_even: bool = False) -> torch.Tensor:
+    """video [B,3,F,H,W] bf16 in [-1,1] (the decoder's output) -> uint8 frames [B,F,H,W,3] on the device, with the reference's
+    rounding points (s2v_video_to_uint8): truncation = export_to_video's `(frame * 255).astype(np.uint8)`, round_half_even =
+    numpy_to_pil's `(images * 255).round().astype("uint8")`."""
+    _chk_bf16(video, "video")
+    if video.dim() != 5 or video.shape[1] != 3 or not video.is_contiguous():
+        raise RuntimeError("video_to_uint8: expected a contiguous [B,3,F,H,W] bf16 tensor")
+    B, _, F, H, W = video.shape
+    out = torch.empty(B, F, H, W, 3, dtype=torch.uint8, device=video.device)
+    lib = _lib.load()
+    _lib.check(lib.s2v_video_to_uint8(video.data_ptr(), out.data_ptr(), B, F, H, W, 1 if round_half_even else 0, _stream()),
+               "s2v_video_to_uint8")
+    return out

@@ -272,8 +272,28 @@ class CustomCogVideoXPipeline:
         return CogVideoXPipelineOutput(frames=video)
 
 
+def _device_uint8_ok(video: torch.Tensor) -> bool:
+    return (video.is_cuda and video.dtype == torch.bfloat16 and video.dim() == 5 and video.shape[1] == 3
+            and (video.shape[3] * video.shape[4]) % 4 == 0)
+
+
 def postprocess_video(video: torch.Tensor, output_type: str = "np"):
-    """D/video_processor.py:89-113: [B,C,F,H,W] in [-1,1] -> per-video [F,H,W,C] in [0,1] (np / pt) or PIL lists."""
+    """D/video_processor.py:89-113: [B,C,F,H,W] in [-1,1] -> per-video [F,H,W,C] in [0,1] (np / pt) or PIL lists.
+
+    Extension: output_type "uint8" returns the np.uint8 array [B,F,H,W,C] that the reference's
+    export_to_video would compute from the "np" output (`(frame * 255).astype(np.uint8)`, D/utils/export_utils.py:177-178),
+    converted on the device by s2v_video_to_uint8 (bit-exact; a quarter of the device->host bytes of the fp32 "np" path).
+    The "pil" path uses the same kernel with numpy_to_pil's rounding."""
+    if output_type in ("uint8", "pil") and _device_uint8_ok(video):
+        from . import ops
+        u8 = ops.video_to_uint8(video.contiguous(), round_half_even=(output_type == "pil")).cpu().numpy()
+        if output_type == "uint8":
+            return u8
+        from PIL import Image
+        return [[Image.fromarray(f) for f in vid] for vid in u8]
+    if output_type == "uint8":
+        raise RuntimeError("postprocess_video(output_type='uint8') needs the decoder's bf16 [B,3,F,H,W] output on a B200 "
+                           "(there is no host path); use 'np' for host tensors")
     outs = []
     for b in range(video.shape[0]):
         frames = (video[b].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)  # [F,C,H,W]
@@ -294,3 +314,39 @@ def postprocess_video(video: torch.Tensor, output_type: str = "np"):
     if output_type == "pt":
         return torch.stack(outs)
     return outs
+
+
+def export_to_video(video_frames, output_video_path: Optional[str] = None, fps: int = 10) -> str:
+    """D/utils/export_utils.py:143-186 (S/video_generate.py:74-75): write [F,H,W,3] frames as an mp4.  Accepts what the reference
+    accepts (float frames in [0,1] -> `(frame * 255).astype(np.uint8)`, or PIL images) and additionally the uint8 frames of
+    postprocess_video(output_type="uint8").  imageio is used when present (the reference's preferred backend), else OpenCV's
+    mp4v writer exactly like the reference's _legacy_export_to_video (:116-141)."""
+    import tempfile
+
+    import numpy as np
+
+    if output_video_path is None:
+        output_video_path = tempfile.NamedTemporaryFile(suffix=".mp4").name
+    first = video_frames[0]
+    if isinstance(first, np.ndarray):
+        frames = [f if f.dtype == np.uint8 else (f * 255).astype(np.uint8) for f in video_frames]
+    else:   # PIL images
+        frames = [np.array(f) for f in video_frames]
+    try:
+        import imageio
+
+        imageio.plugins.ffmpeg.get_exe()
+        with imageio.get_writer(output_video_path, fps=fps) as writer:
+            for f in frames:
+                writer.append_data(f)
+        return output_video_path
+    except (ImportError, AttributeError, RuntimeError):
+        pass
+    import cv2
+
+    h, w, _ = frames[0].shape
+    writer = cv2.VideoWriter(output_video_path, cv2.VideoWriter_fourcc(*"mp4v"), fps=fps, frameSize=(w, h))
+    for f in frames:
+        writer.write(cv2.cvtColor(np.ascontiguousarray(f), cv2.COLOR_RGB2BGR))
+    writer.release()
+    return output_video_path

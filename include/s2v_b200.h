@@ -246,6 +246,13 @@ S2V_API int s2v_vae_volume_to_video(const void* vol, void* video, int32_t T, int
 /* In-place seam ramp of tiled_decode (blend_v / blend_h, autoencoder_kl_cogvideox.py:1284-1298) on bf16 tensors with
  * arbitrary element strides (outer, blended axis, other axis): b[o,y,x] = a[o, a_len-extent+y, x]*(1-y/extent) + b[o,y,x]*(y/extent),
  * with torch's bf16 rounding points. */
+/* Device-side post-processing of the decoded video (replaces the host chain D/video_processor.py:89-113 postprocess_video ->
+ * D/image_processor.py:227-239 denormalize -> :196-208 pt_to_numpy -> D/utils/export_utils.py:177-178 `(frame * 255).astype(uint8)`,
+ * or :133-150 numpy_to_pil's `(images * 255).round().astype("uint8")`), bit-exact with the reference's bf16 / fp32 rounding points.
+ * video [B, 3, F, H, W] bf16 in [-1, 1] -> frames [B, F, H, W, 3] uint8.  round_mode 0 = truncate (export_to_video),
+ * 1 = round half to even (PIL path).  H*W must be a multiple of 4. */
+S2V_API int s2v_video_to_uint8(const void* video, void* frames, int32_t B, int32_t F, int32_t H, int32_t W, int32_t round_mode,
+                               void* stream);
 S2V_API int s2v_vae_blend(const void* a, void* b, int64_t n_outer, int32_t extent, int32_t n_other, int32_t a_len, int64_t a_so,
                           int64_t a_sy, int64_t a_sx, int64_t b_so, int64_t b_sy, int64_t b_sx, void* stream);
 

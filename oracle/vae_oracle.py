@@ -299,3 +299,175 @@ def decode_latents(p: Params, cfg: VaeConfig, latents: torch.Tensor, use_tiling:
     z = latents.permute(0, 2, 1, 3, 4)
     z = 1 / cfg.scaling_factor * z
     return decode(p, cfg, z, use_tiling)
+
+
+# ----------------------------------------------------------------------------------------------- host glue after the decoder
+def frames_uint8(video: torch.Tensor, round_half_even: bool = False):
+    """uint8 frames [B,F,H,W,C] the reference derives from the decoder output `video` [B,C,F,H,W] (any float dtype):
+    D/video_processor.py:89-113 postprocess_video -> D/image_processor.py:227-239 denormalize `(x / 2 + 0.5).clamp(0, 1)`
+    (two tensor ops in the video's dtype, so bf16 rounds twice) -> :196-208 pt_to_numpy (`.float().numpy()`), then either
+    D/utils/export_utils.py:177-178 `(frame * 255).astype(np.uint8)` (truncation; the path S/video_generate.py:74-75 takes)
+    or D/image_processor.py:133-150 numpy_to_pil `(images * 255).round().astype("uint8")` (round half to even)."""
+    import numpy as np
+
+    outs = []
+    for b in range(video.shape[0]):
+        frames = video[b].permute(1, 0, 2, 3)                       # [F,C,H,W]
+        frames = (frames / 2 + 0.5).clamp(0, 1)
+        arr = frames.cpu().permute(0, 2, 3, 1).float().numpy()      # [F,H,W,C] fp32
+        arr = arr * 255
+        outs.append((arr.round() if round_half_even else arr).astype(np.uint8))
+    return np.stack(outs)
+
+
+# =============================================================================================== encoder (SURVEY §8f row 3)
+# CogVideoXEncoder3D (A/:658-814) for the reference-image path of S/video_generate.py:26-38: ONE frame per call, so the
+# temporal compression of CogVideoXDownsample3D (D/models/downsampling.py:322-343) is the identity and every causal conv sees
+# its single frame three times.  Multi-frame (video) encoding is outside the subject-to-video inference path.
+def encoder_param_shapes(cfg: VaeConfig, in_channels: int = 3) -> Dict[str, Tuple[int, ...]]:
+    """Names and shapes of the encoder parameters (CogVideoXEncoder3D.__init__, A/:682-753)."""
+    ch = list(cfg.block_out_channels)
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def conv3(name, cin, cout, k):
+        shapes[f"{name}.conv.weight"] = (cout, cin, k, k, k)
+        shapes[f"{name}.conv.bias"] = (cout,)
+
+    def resnet(name, cin, cout):   # spatial_norm_dim=None -> plain nn.GroupNorm (A/:241-243)
+        shapes[f"{name}.norm1.weight"] = (cin,)
+        shapes[f"{name}.norm1.bias"] = (cin,)
+        conv3(f"{name}.conv1", cin, cout, 3)
+        shapes[f"{name}.norm2.weight"] = (cout,)
+        shapes[f"{name}.norm2.bias"] = (cout,)
+        conv3(f"{name}.conv2", cout, cout, 3)
+        if cin != cout:
+            shapes[f"{name}.conv_shortcut.weight"] = (cout, cin, 1, 1, 1)
+            shapes[f"{name}.conv_shortcut.bias"] = (cout,)
+
+    conv3("encoder.conv_in", in_channels, ch[0], 3)
+    prev = ch[0]
+    for b, c in enumerate(ch):
+        for i in range(cfg.layers_per_block):
+            resnet(f"encoder.down_blocks.{b}.resnets.{i}", prev if i == 0 else c, c)
+        if b != len(ch) - 1:
+            shapes[f"encoder.down_blocks.{b}.downsamplers.0.conv.weight"] = (c, c, 3, 3)
+            shapes[f"encoder.down_blocks.{b}.downsamplers.0.conv.bias"] = (c,)
+        prev = c
+    for i in range(2):
+        resnet(f"encoder.mid_block.resnets.{i}", ch[-1], ch[-1])
+    shapes["encoder.norm_out.weight"] = (ch[-1],)
+    shapes["encoder.norm_out.bias"] = (ch[-1],)
+    conv3("encoder.conv_out", ch[-1], 2 * cfg.latent_channels, 3)
+    return shapes
+
+
+def synth_encoder_params(cfg: VaeConfig, seed: int = 0) -> Params:
+    g = torch.Generator().manual_seed(seed)
+    p: Params = {}
+    for name, shape in encoder_param_shapes(cfg).items():
+        if "norm" in name and name.endswith("weight") and len(shape) == 1:
+            p[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif "norm" in name and name.endswith("bias"):
+            p[name] = 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("bias"):
+            p[name] = 0.05 * torch.randn(shape, generator=g)
+        else:
+            p[name] = torch.randn(shape, generator=g) / (int(np.prod(shape[1:])) ** 0.5)
+    return p
+
+
+def resnet_block_plain(p: Params, name: str, x: torch.Tensor, groups: int, eps: float) -> torch.Tensor:
+    """CogVideoXResnetBlock3D.forward with zq=None, temb=None (A/:278-319), no conv cache (single call)."""
+    h = F.silu(F.group_norm(x, groups, p[f"{name}.norm1.weight"], p[f"{name}.norm1.bias"], eps))
+    h, _ = causal_conv3d(p, f"{name}.conv1", h, None)
+    h = F.silu(F.group_norm(h, groups, p[f"{name}.norm2.weight"], p[f"{name}.norm2.bias"], eps))
+    h, _ = causal_conv3d(p, f"{name}.conv2", h, None)
+    if f"{name}.conv_shortcut.weight" in p:
+        x = F.conv3d(x, p[f"{name}.conv_shortcut.weight"], p[f"{name}.conv_shortcut.bias"])
+    return h + x
+
+
+def downsample3d_single_frame(p: Params, name: str, x: torch.Tensor) -> torch.Tensor:
+    """CogVideoXDownsample3D.forward (D/models/downsampling.py:322-353) for ONE frame: with an odd frame count the first frame
+    is kept and `x_rest` is empty (:329-335), so compress_time changes nothing; then F.pad (0,1,0,1) and the stride-2 3x3
+    Conv2d applied per frame."""
+    b, c, t, h, w = x.shape
+    assert t == 1, "the oracle covers the single-frame (reference image) path"
+    y = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
+    y = y.permute(0, 2, 1, 3, 4).reshape(b * t, c, h + 1, w + 1)
+    y = F.conv2d(y, p[f"{name}.conv.weight"], p[f"{name}.conv.bias"], stride=2)
+    return y.reshape(b, t, y.shape[1], y.shape[2], y.shape[3]).permute(0, 2, 1, 3, 4)
+
+
+def encoder_forward(p: Params, cfg: VaeConfig, sample: torch.Tensor) -> torch.Tensor:
+    """CogVideoXEncoder3D.forward (A/:755-814) -> the 2*latent_channels moments (mean | logvar)."""
+    G, eps = cfg.norm_num_groups, cfg.norm_eps
+    h, _ = causal_conv3d(p, "encoder.conv_in", sample, None)
+    n = len(cfg.block_out_channels)
+    for b in range(n):
+        for i in range(cfg.layers_per_block):
+            h = resnet_block_plain(p, f"encoder.down_blocks.{b}.resnets.{i}", h, G, eps)
+        if b != n - 1:
+            h = downsample3d_single_frame(p, f"encoder.down_blocks.{b}.downsamplers.0", h)
+    for i in range(2):
+        h = resnet_block_plain(p, f"encoder.mid_block.resnets.{i}", h, G, eps)
+    h = F.silu(F.group_norm(h, G, p["encoder.norm_out.weight"], p["encoder.norm_out.bias"], 1e-6))   # A/:751 eps is literal 1e-6
+    h, _ = causal_conv3d(p, "encoder.conv_out", h, None)
+    return h
+
+
+def tiled_encode(p: Params, cfg: VaeConfig, x: torch.Tensor) -> torch.Tensor:
+    """AutoencoderKLCogVideoX.tiled_encode (A/:1300-1372) for one frame: overlapping sample tiles, each through the encoder,
+    blended over the latent overlap and cropped to the row / column limits."""
+    oh = int(cfg.tile_sample_min_height * (1 - cfg.tile_overlap_factor_height))
+    ow = int(cfg.tile_sample_min_width * (1 - cfg.tile_overlap_factor_width))
+    bh = int(cfg.tile_latent_min_height * cfg.tile_overlap_factor_height)
+    bw = int(cfg.tile_latent_min_width * cfg.tile_overlap_factor_width)
+    lh, lw = cfg.tile_latent_min_height - bh, cfg.tile_latent_min_width - bw
+    H, W = x.shape[3], x.shape[4]
+    rows = []
+    for i in range(0, H, oh):
+        rows.append([encoder_forward(p, cfg, x[:, :, :, i:i + cfg.tile_sample_min_height, j:j + cfg.tile_sample_min_width])
+                     for j in range(0, W, ow)])
+    out_rows = []
+    for i, row in enumerate(rows):
+        out = []
+        for j, tile in enumerate(row):
+            if i > 0:
+                tile = blend_v(rows[i - 1][j], tile, bh)
+            if j > 0:
+                tile = blend_h(row[j - 1], tile, bw)
+            out.append(tile[:, :, :, :lh, :lw])
+        out_rows.append(torch.cat(out, dim=4))
+    return torch.cat(out_rows, dim=3)
+
+
+def encode_moments(p: Params, cfg: VaeConfig, x: torch.Tensor, use_tiling: bool = True) -> torch.Tensor:
+    """AutoencoderKLCogVideoX.encode/_encode (A/:1177-1229) for x [B, 3, 1, H, W]: the moments tensor the reference wraps in
+    DiagonalGaussianDistribution (quant_conv is None for CogVideoX)."""
+    assert x.shape[2] == 1
+    outs = []
+    for xs in x.split(1):   # use_slicing
+        if use_tiling and (x.shape[4] > cfg.tile_sample_min_width or x.shape[3] > cfg.tile_sample_min_height):
+            outs.append(tiled_encode(p, cfg, xs))
+        else:
+            outs.append(encoder_forward(p, cfg, xs))
+    return torch.cat(outs)
+
+
+def gaussian_sample(moments: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """DiagonalGaussianDistribution (D/models/autoencoders/vae.py:691-744): mean, logvar = chunk(2, dim=1); logvar clamped to
+    [-30, 20]; std = exp(0.5 logvar); sample = mean + std * noise."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    return mean + torch.exp(0.5 * logvar) * noise
+
+
+def reference_image_latents(p: Params, cfg: VaeConfig, image_u8: "np.ndarray", noise: torch.Tensor, use_tiling: bool = True,
+                            dtype=torch.float32) -> torch.Tensor:
+    """S/video_generate.py:26-38: uint8 RGB [H, W, 3] -> float / 255 * 2 - 1 -> [1, 3, 1, H, W] -> vae.encode -> sample *
+    scaling_factor -> [1, 1, C, h, w] (the `ref_img_states` pipeline argument)."""
+    x = torch.from_numpy(np.expand_dims(image_u8, 0)).float() / 255.0 * 2.0 - 1.0
+    x = x.permute(0, 3, 1, 2).unsqueeze(0).permute(0, 2, 1, 3, 4).to(dtype)
+    lat = gaussian_sample(encode_moments(p, cfg, x, use_tiling), noise) * cfg.scaling_factor
+    return lat.permute(0, 2, 1, 3, 4)

@@ -308,6 +308,65 @@ def gen_vae():
     torch.save(fix, os.path.join(HERE, "vae_tiny.pt"))
 
 
+# ------------------------------------------------------------------ I. VAE encoder, reference-image path
+def gen_vae_enc():
+    """The reference AutoencoderKLCogVideoX.encode on ONE frame (S/video_generate.py:26-38) with seeded encoder weights: untiled,
+    and tiled (3x3 overlapping sample tiles, blended in latent space) as S/inference.py:206-207 enables it; plus the
+    reference-image preparation chain end to end with a fixed noise draw."""
+    from diffusers.models.autoencoders.autoencoder_kl_cogvideox import AutoencoderKLCogVideoX
+
+    from oracle import vae_oracle as V
+
+    cfg = V.VaeConfig(block_out_channels=(64, 128, 128, 128), layers_per_block=1, sample_height=64, sample_width=96,
+                      scaling_factor=0.7)
+    params = V.synth_encoder_params(cfg, seed=61)
+    vae = AutoencoderKLCogVideoX(block_out_channels=cfg.block_out_channels, layers_per_block=cfg.layers_per_block,
+                                 latent_channels=16, sample_height=cfg.sample_height, sample_width=cfg.sample_width,
+                                 scaling_factor=cfg.scaling_factor, temporal_compression_ratio=4).float().eval()
+    missing, unexpected = vae.load_state_dict(params, strict=False)
+    assert not unexpected and all(k.startswith("decoder.") for k in missing), (unexpected, [k for k in missing if not k.startswith("decoder.")][:5])
+    assert set(params) == {k for k in vae.state_dict() if k.startswith("encoder.")}
+    g = torch.Generator().manual_seed(62)
+    img = torch.randint(0, 256, (64, 96, 3), generator=g, dtype=torch.uint8).numpy()
+    x = torch.from_numpy(np.expand_dims(img, 0)).float() / 255.0 * 2.0 - 1.0                   # S/video_generate.py:29-33
+    x = x.permute(0, 3, 1, 2).unsqueeze(0).permute(0, 2, 1, 3, 4)
+    fix = dict(cfg=cfg.__dict__, seed=61, image=img, weight_checksum=float(sum(v.double().sum() for v in params.values())))
+    with torch.no_grad():
+        fix["moments_untiled"] = vae.encode(x).latent_dist.parameters
+        fix["moments_tile"] = vae.encode(x[:, :, :, :32, :48]).latent_dist.parameters        # one tile-sized call
+        vae.enable_slicing()
+        vae.enable_tiling()
+        dist = vae.encode(x).latent_dist
+        fix["moments_tiled"] = dist.parameters
+        gen = torch.Generator().manual_seed(63)
+        fix["ref_img_states"] = (dist.sample(gen) * vae.config.scaling_factor).permute(0, 2, 1, 3, 4)   # S/video_generate.py:36-38
+        fix["noise"] = torch.randn(dist.mean.shape, generator=torch.Generator().manual_seed(63))
+    print("vae_enc", {k: tuple(v.shape) for k, v in fix.items() if isinstance(v, torch.Tensor)}, float(fix["moments_tiled"].abs().mean()))
+    torch.save(fix, os.path.join(HERE, "vae_enc_tiny.pt"))
+
+
+# ------------------------------------------------------------------ H. host glue after the decoder (SURVEY §8f row 4)
+def gen_post():
+    """The reference's own VideoProcessor.postprocess_video (np and pil outputs) and export_to_video's uint8 conversion on a
+    seeded bf16 video that includes out-of-range values and exact rounding ties."""
+    import numpy as np
+    from diffusers.video_processor import VideoProcessor
+
+    g = torch.Generator().manual_seed(71)
+    v = (torch.randn(2, 3, 3, 8, 12, generator=g) * 0.8)
+    ties = torch.tensor([-1.0, 1.0, 0.0, -0.5, 0.5, 1.5, -1.5, 1 / 255.0 - 1.0, 0.00390625, 0.99609375, -0.99609375, 0.5 / 255.0])
+    v.view(-1)[: ties.numel()] = ties
+    v = v.to(torch.bfloat16)
+    vp = VideoProcessor(vae_scale_factor=8)
+    as_np = vp.postprocess_video(video=v, output_type="np")                     # [B,F,H,W,C] fp32 in [0,1]
+    trunc = np.stack([np.stack([(frame * 255).astype(np.uint8) for frame in vid]) for vid in as_np])   # export_utils.py:177-178
+    pil = vp.postprocess_video(video=v, output_type="pil")
+    rounded = np.stack([np.stack([np.array(im) for im in vid]) for vid in pil])
+    np.savez_compressed(os.path.join(HERE, "postprocess.npz"), video_bf16_bits=v.view(torch.int16).numpy(), as_np=as_np, trunc=trunc,
+                        rounded=rounded)
+    print("postprocess.npz", trunc.shape, int((trunc != rounded).sum()), "pixels differ between the two roundings")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     which = sys.argv[1:] or ["sched", "rope", "block", "transformer", "pipe", "vae", "dpm"]
@@ -318,3 +377,5 @@ if __name__ == "__main__":
     if "pipe" in which: gen_pipe_loop()
     if "vae" in which: gen_vae()
     if "dpm" in which: gen_dpm()
+    if "post" in which: gen_post()
+    if "vae_enc" in which: gen_vae_enc()

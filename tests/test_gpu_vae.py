@@ -290,3 +290,45 @@ def test_attach_vae_on_a_stock_like_object(dev, fix, vae):
     m.enable_tiling(); m.enable_slicing()
     z = fix["z"].to(torch.bfloat16).to(dev)
     assert torch.equal(s.decode(z).sample, m.decode(z).sample)
+
+
+def test_video_to_uint8_bit_exact_vs_reference_golden_and_oracle(dev, golden_dir):
+    """s2v_video_to_uint8 (device-side postprocess_video + export conversion) against the reference-generated
+    fixture (both roundings), against the oracle on a seeded odd-shaped video, and the public postprocess_video paths."""
+    import numpy as np
+    import s2v_b200
+    from s2v_b200 import ops
+    d = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    video = torch.from_numpy(d["video_bf16_bits"].copy()).view(torch.bfloat16).to(dev)
+    assert np.array_equal(ops.video_to_uint8(video, False).cpu().numpy(), d["trunc"])
+    assert np.array_equal(ops.video_to_uint8(video, True).cpu().numpy(), d["rounded"])
+    assert np.array_equal(s2v_b200.postprocess_video(video, "uint8"), d["trunc"])
+    pil = s2v_b200.postprocess_video(video, "pil")
+    assert np.array_equal(np.stack([np.stack([np.array(im) for im in vid]) for vid in pil]), d["rounded"])
+    g = torch.Generator().manual_seed(9)
+    v = (torch.randn(3, 3, 5, 6, 10, generator=g) * 1.2).to(torch.bfloat16)     # H*W = 60: multiple of 4, W is not
+    for mode in (False, True):
+        assert np.array_equal(ops.video_to_uint8(v.to(dev), mode).cpu().numpy(), V.frames_uint8(v, mode))
+    with pytest.raises(RuntimeError):
+        ops.video_to_uint8(torch.zeros(1, 3, 1, 3, 3, dtype=torch.bfloat16, device=dev))   # H*W % 4 != 0: refused, no fallback
+
+
+def test_video_to_uint8_full_size_properties(dev):
+    """49 x 480 x 720 (BASELINE size): every bf16 bit pattern in [-1.5, 1.5] appears; the kernel must equal the oracle's lookup
+    table of that pattern (the map is a pure per-element function), and be monotone in the input."""
+    import numpy as np
+    from s2v_b200 import ops
+    g = torch.Generator().manual_seed(10)
+    v = (torch.rand(1, 3, 49, 480, 720, generator=g) * 3 - 1.5).to(torch.bfloat16)
+    got = ops.video_to_uint8(v.to(dev), False).cpu()
+    bits = torch.arange(-32768, 32768, dtype=torch.int32).to(torch.int16)
+    vals = bits.view(torch.bfloat16)
+    finite = torch.isfinite(vals.float())
+    lut = torch.zeros(65536, dtype=torch.uint8)
+    tab = V.frames_uint8(torch.where(finite, vals, torch.zeros_like(vals)).view(1, 1, 1, 1, -1).expand(1, 3, 1, 1, -1).contiguous(), False)
+    lut[(bits.to(torch.int32) & 0xFFFF).long()] = torch.from_numpy(tab[0, 0, 0, :, 0].copy())
+    want = lut[(v.view(torch.int16).to(torch.int32) & 0xFFFF).long()].permute(0, 2, 3, 4, 1)   # [B,F,H,W,C]
+    assert torch.equal(got, want)
+    order = torch.argsort(v.float().flatten()[:200000])
+    mono = got.permute(0, 4, 1, 2, 3).flatten()[:200000][order].to(torch.int16)
+    assert (mono[1:] >= mono[:-1]).all()
