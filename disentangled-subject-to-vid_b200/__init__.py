@@ -23,6 +23,6 @@ from .modules import (  # noqa: F401
 )
 from .pipeline import CogVideoXPipelineOutput, CustomCogVideoXPipeline, export_to_video, postprocess_video  # noqa: F401
 from .scheduler import CogVideoXDDIMScheduler, CogVideoXDPMScheduler  # noqa: F401
-from .vae import AutoencoderKLCogVideoX, attach_vae  # noqa: F401
+from .vae import AutoencoderKLCogVideoX, attach_vae, encode_reference_image  # noqa: F401
 
 __version__ = "0.1.0"

@@ -92,6 +92,8 @@ SIGNATURES = {
     "s2v_vae_spatialnorm_silu": [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "s2v_vae_upsample_nearest": [_vp, _vp, C.POINTER(C.c_int32), _i32, _i32, _i32, _i32, _vp],
     "s2v_vae_volume_to_video": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "s2v_vae_groupnorm_silu": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "s2v_vae_subsample2": [_vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "s2v_video_to_uint8": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "s2v_vae_blend": [_vp, _vp, _i64, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _vp],
 }

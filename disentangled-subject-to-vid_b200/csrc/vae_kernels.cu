@@ -173,9 +173,17 @@ __global__ void __launch_bounds__(256) spatialnorm_silu_kernel(const bf16* __res
             v_unpack8(__ldg(reinterpret_cast<const uint4*>(x + off)), f);
             v_unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + v * 8)), gm);
             v_unpack8(__ldg(reinterpret_cast<const uint4*>(beta + v * 8)), bt);
-            const long long lrow = ((long long)fm.src[t] * hl + ((hp - 1) >> lsh)) * wl + ((wp - 1) >> lsw);
-            v_unpack8(__ldg(reinterpret_cast<const uint4*>(yb + lrow * 2 * C + v * 8)), yy);
-            v_unpack8(__ldg(reinterpret_cast<const uint4*>(yb + lrow * 2 * C + C + v * 8)), bb);
+            if (yb) {
+                const long long lrow = ((long long)fm.src[t] * hl + ((hp - 1) >> lsh)) * wl + ((wp - 1) >> lsw);
+                v_unpack8(__ldg(reinterpret_cast<const uint4*>(yb + lrow * 2 * C + v * 8)), yy);
+                v_unpack8(__ldg(reinterpret_cast<const uint4*>(yb + lrow * 2 * C + C + v * 8)), bb);
+            } else {   // plain GroupNorm + SiLU (the encoder's resnets: spatial_norm_dim=None)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    yy[j] = 1.f;
+                    bb[j] = 0.f;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int g = (v * 8 + j) / cpg;
@@ -205,6 +213,28 @@ __global__ void __launch_bounds__(256) upsample_nearest_kernel(const bf16* __res
         if (hp >= 1 && hp <= H && wp >= 1 && wp <= W)
             o = __ldg(reinterpret_cast<const uint4*>(x + ((long long)((fm.src[t] + 2) * Hpi + ((hp - 1) >> 1) + 1) * Wpi + ((wp - 1) >> 1) + 1) * C +
                                                      v * 8));
+        *reinterpret_cast<uint4*>(out + ((long long)((t + 2) * Hp + hp) * Wp + wp) * C + v * 8) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stride-2 subsample
+// CogVideoXDownsample3D's conv (D/models/downsampling.py:345-350) is F.pad(0,1,0,1) + a stride-2 3x3 Conv2d: output (y, x) is
+// the stride-1 'same' convolution at (2y + 1, 2x + 1) — whose bottom / right neighbours at the edge are the zero ring of the
+// padded volume, exactly the reference's padding.  The stride-1 product runs on the implicit-GEMM conv; this kernel keeps the
+// odd positions: out[t, y, x, :] = in[t, 2y + 1, 2x + 1, :] (interior coordinates), zero ring.
+__global__ void __launch_bounds__(256) subsample2_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int T, int H_in, int W_in, int C) {
+    const int H = H_in / 2, W = W_in / 2, Hp = H + 2, Wp = W + 2, Hpi = H_in + 2, Wpi = W_in + 2, vpp = C >> 3;
+    const long long nvec = (long long)T * Hp * Wp * vpp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vpp);
+        long long r = i / vpp;
+        const int wp = (int)(r % Wp);
+        r /= Wp;
+        const int hp = (int)(r % Hp);
+        const int t = (int)(r / Hp);
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (hp >= 1 && hp <= H && wp >= 1 && wp <= W)
+            o = __ldg(reinterpret_cast<const uint4*>(x + ((long long)((t + 2) * Hpi + 2 * hp) * Wpi + 2 * wp) * C + v * 8));
         *reinterpret_cast<uint4*>(out + ((long long)((t + 2) * Hp + hp) * Wp + wp) * C + v * 8) = o;
     }
 }
@@ -359,6 +389,33 @@ extern "C" int s2v_vae_spatialnorm_silu(const void* x, void* out, const float* s
         static_cast<const bf16*>(x), static_cast<bf16*>(out), stats, static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta),
         static_cast<const bf16*>(yb), fm, T, H, W, C, G, hl, wl, lsh, lsw);
     return check_launch("spatialnorm_silu_kernel");
+}
+
+extern "C" int s2v_vae_groupnorm_silu(const void* x, void* out, const float* stats, const void* gamma, const void* beta, int32_t T,
+                                      int32_t H, int32_t W, int32_t C, int32_t G, void* stream) {
+    if (!x || !out || !stats || !gamma || !beta) return set_error(S2V_E_BADARG, "s2v_vae_groupnorm_silu: null pointer");
+    if (T <= 0 || T > 32 || (C % 8) || (C % G) || H <= 0 || W <= 0)
+        return set_error(S2V_E_UNSUPPORTED, "s2v_vae_groupnorm_silu: T <= 32, C % 8 == 0, C % G == 0");
+    int rc = ensure_device();
+    if (rc) return rc;
+    FrameMap fm;
+    for (int t = 0; t < 32; ++t) fm.src[t] = 0;
+    const long long nvec = (long long)T * (H + 2) * (W + 2) * (C / 8);
+    spatialnorm_silu_kernel<<<grid_for(nvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(x), static_cast<bf16*>(out), stats, static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta),
+        nullptr, fm, T, H, W, C, G, H, W, 0, 0);
+    return check_launch("spatialnorm_silu_kernel");
+}
+
+extern "C" int s2v_vae_subsample2(const void* x, void* out, int32_t T, int32_t H_in, int32_t W_in, int32_t C, void* stream) {
+    if (!x || !out) return set_error(S2V_E_BADARG, "s2v_vae_subsample2: null pointer");
+    if (T <= 0 || H_in < 2 || W_in < 2 || (C % 8)) return set_error(S2V_E_UNSUPPORTED, "s2v_vae_subsample2: H, W >= 2 and C % 8 == 0");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const long long nvec = (long long)T * (H_in / 2 + 2) * (W_in / 2 + 2) * (C / 8);
+    subsample2_kernel<<<grid_for(nvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(out), T,
+                                                                                         H_in, W_in, C);
+    return check_launch("subsample2_kernel");
 }
 
 extern "C" int s2v_vae_upsample_nearest(const void* x, void* out, const int32_t* frame_src, int32_t T_out, int32_t H_in, int32_t W_in,

@@ -115,6 +115,59 @@ class CogVideoXDecoder3D(nn.Module):
     forward = _no_eager("CogVideoXDecoder3D")
 
 
+class _EncResnet(nn.Module):   # CogVideoXResnetBlock3D with spatial_norm_dim=None: plain GroupNorm (A/:241-243)
+    def __init__(self, in_channels: int, out_channels: int, groups: int = 32):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(num_channels=in_channels, num_groups=groups, eps=1e-6)
+        self.norm2 = nn.GroupNorm(num_channels=out_channels, num_groups=groups, eps=1e-6)
+        self.conv1 = CogVideoXCausalConv3d(in_channels, out_channels, 3)
+        self.conv2 = CogVideoXCausalConv3d(out_channels, out_channels, 3)
+        if in_channels != out_channels:
+            self.conv_shortcut = nn.Conv3d(in_channels, out_channels, 1)
+
+    forward = _no_eager("CogVideoXResnetBlock3D")
+
+
+class CogVideoXDownsample3D(nn.Module):
+    def __init__(self, channels: int, compress_time: bool):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=0)
+        self.compress_time = compress_time
+
+    forward = _no_eager("CogVideoXDownsample3D")
+
+
+class _EncBlock(nn.Module):
+    def __init__(self, cin, cout, n, groups, downsample: Optional[bool]):
+        super().__init__()
+        self.resnets = nn.ModuleList([_EncResnet(cin if i == 0 else cout, cout, groups) for i in range(n)])
+        self.downsamplers = None if downsample is None else nn.ModuleList([CogVideoXDownsample3D(cout, downsample)])
+
+    forward = _no_eager("CogVideoXDownBlock3D / CogVideoXMidBlock3D")
+
+
+class CogVideoXEncoder3D(nn.Module):
+    """Parameter tree of D/.../autoencoder_kl_cogvideox.py:682-753."""
+
+    def __init__(self, in_channels=3, out_channels=16, block_out_channels=(128, 256, 256, 512), layers_per_block=3,
+                 norm_num_groups=32, temporal_compression_ratio=4):
+        super().__init__()
+        ch = list(block_out_channels)
+        self.conv_in = CogVideoXCausalConv3d(in_channels, ch[0], 3)
+        t_levels = int(round(math.log2(float(temporal_compression_ratio))))
+        blocks, prev = [], ch[0]
+        for i, c in enumerate(ch):
+            last = i == len(ch) - 1
+            blocks.append(_EncBlock(prev, c, layers_per_block, norm_num_groups, None if last else (i < t_levels)))
+            prev = c
+        self.down_blocks = nn.ModuleList(blocks)
+        self.mid_block = _EncBlock(ch[-1], ch[-1], 2, norm_num_groups, None)
+        self.norm_out = nn.GroupNorm(norm_num_groups, ch[-1], eps=1e-6)
+        self.conv_out = CogVideoXCausalConv3d(ch[-1], 2 * out_channels, 3)
+
+    forward = _no_eager("CogVideoXEncoder3D")
+
+
 # ------------------------------------------------------------------------------------------------ engine
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -335,6 +388,131 @@ class VaeDecoderEngine:
         return new_cache, T
 
 
+class VaeEncoderEngine:
+    """`CogVideoXEncoder3D.forward` (autoencoder_kl_cogvideox.py:755-814) for ONE frame — the reference-image path of
+    S/video_generate.py:26-38 — on the same padded channels-last volumes and kernels as the decoder: implicit-GEMM causal convs
+    (a single frame is its own temporal context), GroupNorm statistics + plain GroupNorm·SiLU, and the downsamplers as a
+    stride-1 3x3 conv followed by the odd-position subsample (= F.pad(0,1,0,1) + stride-2 Conv2d; compress_time is the identity
+    on one frame, D/models/downsampling.py:329-335).  Multi-frame video encoding is not on the inference path and is refused."""
+
+    CPAD = 8     # image channels padded to 8 so the explicit im2col of conv_in has K = 27 * 8 (a multiple of 8)
+
+    def __init__(self, state: Dict[str, torch.Tensor], block_out_channels, layers_per_block: int, norm_num_groups: int,
+                 latent_channels: int = 16, in_channels: int = 3, prefix: str = "encoder."):
+        self.ch = list(block_out_channels)
+        self.layers = int(layers_per_block)
+        self.G = int(norm_num_groups)
+        self.zc = int(latent_channels)
+        self.cin = int(in_channels)
+        p = {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix)}
+        if not p:
+            raise RuntimeError("no encoder.* parameters found")
+        dev = next(iter(p.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("VaeEncoderEngine needs the VAE on a CUDA (B200) device; there is no CPU path")
+        for k, v in p.items():
+            if v.dtype != BF16:
+                raise RuntimeError(f"the B200 VAE engine computes in bfloat16; got {v.dtype} for {k} (use vae.to(torch.bfloat16))")
+        if self.cin > self.CPAD:
+            raise RuntimeError("at most 8 image channels")
+        for c in self.ch:
+            if c % 64 or 256 % (c // 8):
+                raise RuntimeError("block_out_channels must be multiples of 64 with C/8 dividing 256 (64, 128, 256, 512)")
+        self.device, self.p = dev, p
+        w, b = p["conv_in.conv.weight"], p["conv_in.conv.bias"]                    # [C0, cin, 3, 3, 3]
+        wp = torch.zeros(w.shape[0], 3, 3, 3, self.CPAD, device=dev, dtype=BF16)
+        wp[..., : self.cin] = w.permute(0, 2, 3, 4, 1)
+        self.conv_in = _Conv(wp.reshape(w.shape[0], 27 * self.CPAD).contiguous(), b.contiguous(), 27 * self.CPAD, w.shape[0], 1)
+        self.conv_out = self._conv3("conv_out")
+        self.norm_out = (p["norm_out.weight"].contiguous(), p["norm_out.bias"].contiguous())
+        self.res: Dict[str, dict] = {}
+        names = [f"down_blocks.{b}.resnets.{i}" for b in range(len(self.ch)) for i in range(self.layers)]
+        names += [f"mid_block.resnets.{i}" for i in range(2)]
+        for n in names:
+            r = dict(norm1=(p[f"{n}.norm1.weight"].contiguous(), p[f"{n}.norm1.bias"].contiguous()), conv1=self._conv3(f"{n}.conv1"),
+                     norm2=(p[f"{n}.norm2.weight"].contiguous(), p[f"{n}.norm2.bias"].contiguous()), conv2=self._conv3(f"{n}.conv2"),
+                     short=None)
+            if f"{n}.conv_shortcut.weight" in p:
+                ws = p[f"{n}.conv_shortcut.weight"]
+                if ws.shape[2:] != (1, 1, 1):
+                    raise RuntimeError("only the 1x1x1 conv_shortcut of CogVideoX is implemented")
+                r["short"] = _Conv(ws.reshape(ws.shape[0], ws.shape[1]).contiguous(), p[f"{n}.conv_shortcut.bias"].contiguous(),
+                                   ws.shape[1], ws.shape[0], 1)
+            self.res[n] = r
+        self.downs = {}
+        for b in range(len(self.ch) - 1):
+            wd = p[f"down_blocks.{b}.downsamplers.0.conv.weight"]                  # [C, C, 3, 3]
+            self.downs[b] = _Conv(wd.permute(0, 2, 3, 1).reshape(wd.shape[0], -1).contiguous(),
+                                  p[f"down_blocks.{b}.downsamplers.0.conv.bias"].contiguous(), wd.shape[1], wd.shape[0], 9)
+        self._bufs: Dict[Tuple, torch.Tensor] = {}
+        self._partial = torch.empty(296 * max(self.ch) * 2, device=dev, dtype=torch.float32)
+
+    def _conv3(self, name) -> _Conv:
+        w, b = self.p[f"{name}.conv.weight"], self.p[f"{name}.conv.bias"]
+        return _Conv(w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], 27 * w.shape[1]).contiguous(), b.contiguous(), w.shape[1], w.shape[0], 27)
+
+    _vol = VaeDecoderEngine._vol
+    _conv = VaeDecoderEngine._conv
+
+    def _gn_silu(self, gb, x: torch.Tensor, out: torch.Tensor, H: int, W: int, Cn: int):
+        stats = torch.empty(self.G * 2, device=self.device, dtype=torch.float32)
+        _call("s2v_vae_groupnorm_stats", x.data_ptr(), self._partial.data_ptr(), stats.data_ptr(), 1, H, W, Cn, self.G, 296, 1e-6, _stream())
+        _call("s2v_vae_groupnorm_silu", x.data_ptr(), out.data_ptr(), stats.data_ptr(), gb[0].data_ptr(), gb[1].data_ptr(), 1, H, W, Cn,
+              self.G, _stream())
+        out[0].copy_(out[2])     # one frame: the causal context is the frame itself, twice (A/:120-127)
+        out[1].copy_(out[2])
+
+    def _resnet(self, name: str, x: torch.Tensor, xtag: str, H: int, W: int) -> Tuple[torch.Tensor, str]:
+        r = self.res[name]
+        cin, cout = r["norm1"][0].numel(), r["conv1"].cout
+        u = self._vol("u", 1, H, W, cin)
+        self._gn_silu(r["norm1"], x, u, H, W, cin)
+        h = self._vol("h", 1, H, W, cout)
+        self._conv(r["conv1"], u, h, 1, H, W)
+        u2 = self._vol("u", 1, H, W, cout)
+        self._gn_silu(r["norm2"], h, u2, H, W, cout)
+        res = x
+        if r["short"] is not None:
+            res = self._vol("s", 1, H, W, cout)
+            self._conv(r["short"], x, res, 1, H, W)
+        otag = "x1" if xtag == "x0" else "x0"
+        out = self._vol(otag, 1, H, W, cout)
+        self._conv(r["conv2"], u2, out, 1, H, W, res=res)
+        return out, otag
+
+    def encode_call(self, img: torch.Tensor, i0: int, j0: int, ht: int, wt: int) -> torch.Tensor:
+        """One encoder forward on the tile (i0, j0, ht, wt) of ONE single-frame sample img [CPAD, 1, H, W] bf16 (channels beyond
+        the real ones zero) -> moments [2 * latent_channels, 1, ht // 2^(L-1), wt // 2^(L-1)] bf16."""
+        Cz, Tz, Hh, Ww = img.shape
+        H, W = ht, wt
+        col = self._vol("col", 1, H, W, 27 * Cz)
+        _call("s2v_vae_latent_im2col", img.data_ptr(), col[2:].data_ptr(), Cz, Tz, Hh, Ww, 0, 1, i0, j0, ht, wt, 1.0, _stream())
+        x, tag = self._vol("x0", 1, H, W, self.ch[0]), "x0"
+        self._conv(self.conv_in, col, x, 1, H, W)
+        for b in range(len(self.ch)):
+            for i in range(self.layers):
+                x, tag = self._resnet(f"down_blocks.{b}.resnets.{i}", x, tag, H, W)
+            if b != len(self.ch) - 1:
+                if H < 2 or W < 2:
+                    raise RuntimeError("image tile too small for the encoder's downsamplers")
+                full = self._vol("dn", 1, H, W, self.ch[b])
+                self._conv(self.downs[b], x, full, 1, H, W)                      # stride-1 3x3 (per-frame conv2d taps)
+                Hin, Win = H, W
+                H, W = Hin // 2, Win // 2
+                tag = "x1" if tag == "x0" else "x0"
+                x = self._vol(tag, 1, H, W, self.ch[b])
+                _call("s2v_vae_subsample2", full.data_ptr(), x.data_ptr(), 1, Hin, Win, self.ch[b], _stream())
+        for i in range(2):
+            x, tag = self._resnet(f"mid_block.resnets.{i}", x, tag, H, W)
+        u = self._vol("u", 1, H, W, self.ch[-1])
+        self._gn_silu(self.norm_out, x, u, H, W, self.ch[-1])
+        o = self._vol("o", 1, H, W, self.conv_out.cout)
+        self._conv(self.conv_out, u, o, 1, H, W)
+        moments = torch.empty(self.conv_out.cout, 1, H, W, device=self.device, dtype=BF16)
+        _call("s2v_vae_volume_to_video", o.data_ptr(), moments.data_ptr(), 1, H, W, self.conv_out.cout, self.conv_out.cout, 1, 0, _stream())
+        return moments
+
+
 def frame_batches(num_frames: int, batch: int) -> List[Tuple[int, int]]:
     """Temporal batching of `_decode` / `tiled_decode` (autoencoder_kl_cogvideox.py:1238-1247, 1414-1419)."""
     n = max(num_frames // batch, 1)
@@ -451,6 +629,125 @@ class _DecodeMixin:
         return DecoderOutput(sample=dec) if return_dict else (dec,)
 
 
+class AutoencoderKLOutput:
+    def __init__(self, latent_dist):
+        self.latent_dist = latent_dist
+
+
+class DiagonalGaussianDistribution:
+    """D/models/autoencoders/vae.py:767-820 (the members the inference path touches): mean | logvar moments, clamped logvar,
+    `sample(generator)` drawing with torch's generator exactly like randn_tensor, `mode()`."""
+
+    def __init__(self, parameters: torch.Tensor, deterministic: bool = False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        gdev = generator.device if generator is not None else self.parameters.device
+        noise = torch.randn(self.mean.shape, generator=generator, device=gdev, dtype=self.parameters.dtype).to(self.parameters.device)
+        return self.mean + self.std * noise
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
+class _EncodeMixin:
+    """encode / _encode / tiled_encode with the reference's control flow (autoencoder_kl_cogvideox.py:1177-1229, 1300-1372),
+    bound to a VaeEncoderEngine; single-frame inputs only (the reference-image path)."""
+
+    def _enc_engine(self) -> VaeEncoderEngine:
+        eng = getattr(self, "_b200_enc_engine", None)
+        if eng is None:
+            cfg = self.config
+            g = (lambda k, d=None: cfg[k] if k in cfg else d) if isinstance(cfg, dict) else (lambda k, d=None: getattr(cfg, k, d))
+            eng = VaeEncoderEngine(self.state_dict(), g("block_out_channels"), g("layers_per_block"), g("norm_num_groups"),
+                                   g("latent_channels", 16), g("in_channels", 3))
+            object.__setattr__(self, "_b200_enc_engine", eng)
+        return eng
+
+    def _encode_image(self, x1: torch.Tensor) -> torch.Tensor:
+        """x1 [C, 1, H, W] -> the engine's channel-padded bf16 image."""
+        eng = self._enc_engine()
+        img = torch.zeros(eng.CPAD, 1, x1.shape[2], x1.shape[3], device=x1.device, dtype=BF16)
+        img[: x1.shape[0]] = x1.to(BF16)
+        return img
+
+    def _encode(self, x: torch.Tensor) -> torch.Tensor:
+        b, c, t, h, w = x.shape
+        if t != 1:
+            raise NotImplementedError("the B200 VAE encoder covers the single-frame reference-image path (S/video_generate.py:26-38); "
+                                      "multi-frame video encoding is not on the inference path")
+        if self.use_tiling and (w > self.tile_sample_min_width or h > self.tile_sample_min_height):
+            return self.tiled_encode(x)
+        eng = self._enc_engine()
+        return torch.stack([eng.encode_call(self._encode_image(x[k]), 0, 0, h, w) for k in range(b)])
+
+    def encode(self, x: torch.Tensor, return_dict: bool = True):
+        if x.dim() != 5:
+            raise ValueError("expected images [batch, channels, frames, height, width]")
+        if self.use_slicing and x.shape[0] > 1:
+            h = torch.cat([self._encode(xs) for xs in x.split(1)])
+        else:
+            h = self._encode(x)
+        posterior = DiagonalGaussianDistribution(h)
+        return AutoencoderKLOutput(latent_dist=posterior) if return_dict else (posterior,)
+
+    def tiled_encode(self, x: torch.Tensor) -> torch.Tensor:
+        b, c, t, height, width = x.shape
+        if t != 1:
+            raise NotImplementedError("the B200 VAE encoder covers the single-frame reference-image path")
+        overlap_height = int(self.tile_sample_min_height * (1 - self.tile_overlap_factor_height))
+        overlap_width = int(self.tile_sample_min_width * (1 - self.tile_overlap_factor_width))
+        blend_extent_height = int(self.tile_latent_min_height * self.tile_overlap_factor_height)
+        blend_extent_width = int(self.tile_latent_min_width * self.tile_overlap_factor_width)
+        row_limit_height = self.tile_latent_min_height - blend_extent_height
+        row_limit_width = self.tile_latent_min_width - blend_extent_width
+        eng = self._enc_engine()
+        imgs = [self._encode_image(x[k]) for k in range(b)]
+        rows = []
+        for i in range(0, height, overlap_height):
+            row = []
+            for j in range(0, width, overlap_width):
+                ht, wt = min(self.tile_sample_min_height, height - i), min(self.tile_sample_min_width, width - j)
+                row.append(torch.stack([eng.encode_call(im, i, j, ht, wt) for im in imgs]))
+            rows.append(row)
+        result_rows = []
+        for i, row in enumerate(rows):
+            result_row = []
+            for j, tile in enumerate(row):
+                if i > 0:
+                    tile = self.blend_v(rows[i - 1][j], tile, blend_extent_height)
+                if j > 0:
+                    tile = self.blend_h(row[j - 1], tile, blend_extent_width)
+                result_row.append(tile[:, :, :, :row_limit_height, :row_limit_width])
+            result_rows.append(torch.cat(result_row, dim=4))
+        return torch.cat(result_rows, dim=3)
+
+
+def encode_reference_image(vae, image, generator: Optional[torch.Generator] = None, dtype=BF16) -> torch.Tensor:
+    """S/video_generate.py:26-38: RGB image (PIL image or uint8 array [H, W, 3]) -> `ref_img_states` [1, 1, C, h, w]:
+    float / 255 * 2 - 1, [1, 3, 1, H, W] in the transformer dtype, vae.encode(...).latent_dist.sample() * scaling_factor, frames
+    moved in front of channels."""
+    import numpy as np
+
+    arr = np.array(image.convert("RGB")) if hasattr(image, "convert") else np.asarray(image)
+    if arr.dtype != np.uint8 or arr.ndim != 3 or arr.shape[2] != 3:
+        raise ValueError("expected an RGB uint8 image [H, W, 3]")
+    dev = next(vae.parameters()).device
+    x = torch.from_numpy(np.expand_dims(arr, axis=0)).float() / 255.0 * 2.0 - 1.0
+    x = x.permute(0, 3, 1, 2).unsqueeze(0).permute(0, 2, 1, 3, 4).to(device=dev, dtype=dtype)
+    cfg = vae.config
+    scaling = cfg["scaling_factor"] if isinstance(cfg, dict) else cfg.scaling_factor
+    lat = vae.encode(x).latent_dist.sample(generator) * scaling
+    return lat.permute(0, 2, 1, 3, 4)
+
+
 def _init_tiling(self, sample_height: int, sample_width: int, n_levels: int):
     """Tiling constants of AutoencoderKLCogVideoX.__init__ (autoencoder_kl_cogvideox.py:1095-1115)."""
     self.use_slicing = False
@@ -465,9 +762,9 @@ def _init_tiling(self, sample_height: int, sample_width: int, n_levels: int):
     self.tile_overlap_factor_width = 1 / 5
 
 
-class AutoencoderKLCogVideoX(_DecodeMixin, nn.Module):
-    """Decoder half of the reference class with the same constructor arguments, config fields, state-dict keys and decode
-    surface.  `encode` is not on the hot path (one reference frame per video) and is not implemented."""
+class AutoencoderKLCogVideoX(_DecodeMixin, _EncodeMixin, nn.Module):
+    """The reference class with the same constructor arguments, config fields, state-dict keys and decode surface; `encode`
+    covers single-frame inputs (the reference image, S/video_generate.py:26-38)."""
 
     def __init__(self, in_channels: int = 3, out_channels: int = 3, block_out_channels=(128, 256, 256, 512), latent_channels: int = 16,
                  layers_per_block: int = 3, act_fn: str = "silu", norm_eps: float = 1e-6, norm_num_groups: int = 32,
@@ -481,8 +778,11 @@ class AutoencoderKLCogVideoX(_DecodeMixin, nn.Module):
             latent_channels=latent_channels, layers_per_block=layers_per_block, act_fn=act_fn, norm_eps=norm_eps,
             norm_num_groups=norm_num_groups, temporal_compression_ratio=temporal_compression_ratio, sample_height=sample_height,
             sample_width=sample_width, scaling_factor=scaling_factor)
+        self.encoder = CogVideoXEncoder3D(in_channels, latent_channels, block_out_channels, layers_per_block, norm_num_groups,
+                                          temporal_compression_ratio)
         self.decoder = CogVideoXDecoder3D(latent_channels, out_channels, block_out_channels, layers_per_block, norm_num_groups,
                                           temporal_compression_ratio)
+        self.quant_conv = None
         self.post_quant_conv = None
         _init_tiling(self, sample_height, sample_width, len(block_out_channels))
 
@@ -507,9 +807,7 @@ class AutoencoderKLCogVideoX(_DecodeMixin, nn.Module):
 
     def invalidate_engine(self):
         object.__setattr__(self, "_b200_engine", None)
-
-    def encode(self, *a, **k):
-        raise NotImplementedError("VAE encode (one reference frame per video) is outside the B200 hot path; use the stock encoder")
+        object.__setattr__(self, "_b200_enc_engine", None)
 
     def forward(self, *a, **k):
         raise RuntimeError("call decode(); AutoencoderKLCogVideoX.forward (encode + decode) is not part of the denoising path")
@@ -521,7 +819,9 @@ def attach_vae(vae: nn.Module) -> nn.Module:
     tile sizes and overlap factors keep coming from the object itself."""
     for name in ("_engine", "_decode_tile", "_decode", "decode", "tiled_decode", "blend_v", "blend_h"):
         object.__setattr__(vae, name, types.MethodType(getattr(_DecodeMixin, name), vae))
+    for name in ("_enc_engine", "_encode_image", "_encode", "encode", "tiled_encode"):
+        object.__setattr__(vae, name, types.MethodType(getattr(_EncodeMixin, name), vae))
     object.__setattr__(vae, "_blend", _DecodeMixin._blend)
-    if getattr(vae, "post_quant_conv", None) is not None:
-        raise NotImplementedError("post_quant_conv is not used by CogVideoX VAEs and is not implemented")
+    if getattr(vae, "post_quant_conv", None) is not None or getattr(vae, "quant_conv", None) is not None:
+        raise NotImplementedError("quant_conv / post_quant_conv are not used by CogVideoX VAEs and are not implemented")
     return vae

@@ -246,6 +246,13 @@ S2V_API int s2v_vae_volume_to_video(const void* vol, void* video, int32_t T, int
 /* In-place seam ramp of tiled_decode (blend_v / blend_h, autoencoder_kl_cogvideox.py:1284-1298) on bf16 tensors with
  * arbitrary element strides (outer, blended axis, other axis): b[o,y,x] = a[o, a_len-extent+y, x]*(1-y/extent) + b[o,y,x]*(y/extent),
  * with torch's bf16 rounding points. */
+/* Encoder side (reference-image VAE encode).  Plain GroupNorm(G) + SiLU of the encoder's resnets
+ * (D/models/autoencoders/autoencoder_kl_cogvideox.py:241-243, 292-305 with zq = None) on a padded channels-last volume, statistics
+ * from s2v_vae_groupnorm_stats; and the odd-position subsample that turns the stride-1 3x3 convolution into
+ * CogVideoXDownsample3D's F.pad(0,1,0,1) + stride-2 Conv2d (D/models/downsampling.py:345-350): out is [T+2, H_in/2+2, W_in/2+2, C]. */
+S2V_API int s2v_vae_groupnorm_silu(const void* x, void* out, const float* stats, const void* gamma, const void* beta, int32_t T,
+                                   int32_t H, int32_t W, int32_t C, int32_t G, void* stream);
+S2V_API int s2v_vae_subsample2(const void* x, void* out, int32_t T, int32_t H_in, int32_t W_in, int32_t C, void* stream);
 /* Device-side post-processing of the decoded video (replaces the host chain D/video_processor.py:89-113 postprocess_video ->
  * D/image_processor.py:227-239 denormalize -> :196-208 pt_to_numpy -> D/utils/export_utils.py:177-178 `(frame * 255).astype(uint8)`,
  * or :133-150 numpy_to_pil's `(images * 255).round().astype("uint8")`), bit-exact with the reference's bf16 / fp32 rounding points.

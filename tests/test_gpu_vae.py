@@ -332,3 +332,101 @@ def test_video_to_uint8_full_size_properties(dev):
     order = torch.argsort(v.float().flatten()[:200000])
     mono = got.permute(0, 4, 1, 2, 3).flatten()[:200000][order].to(torch.int16)
     assert (mono[1:] >= mono[:-1]).all()
+
+
+# ------------------------------------------------------------------------------------------- encoder
+@pytest.fixture(scope="module")
+def enc(dev, golden_dir):
+    import s2v_b200
+    fx = torch.load(os.path.join(golden_dir, "vae_enc_tiny.pt"), weights_only=False)
+    cfg = V.VaeConfig(**fx["cfg"])
+    p = V.synth_encoder_params(cfg, seed=fx["seed"])
+    m = s2v_b200.AutoencoderKLCogVideoX(block_out_channels=cfg.block_out_channels, layers_per_block=cfg.layers_per_block,
+                                        sample_height=cfg.sample_height, sample_width=cfg.sample_width, scaling_factor=cfg.scaling_factor)
+    missing, unexpected = m.load_state_dict(p, strict=False)
+    assert not unexpected and all(k.startswith("decoder.") for k in missing)
+    return m.to(torch.bfloat16).to(dev), cfg, p, fx
+
+
+def _img_tensor(img):
+    import numpy as np
+    x = torch.from_numpy(np.expand_dims(img, 0)).float() / 255.0 * 2.0 - 1.0
+    return x.permute(0, 3, 1, 2).unsqueeze(0).permute(0, 2, 1, 3, 4)
+
+
+@pytest.mark.parametrize("mode", ["tile", "untiled", "tiled"])
+def test_encode_vs_reference_golden(dev, enc, mode):
+    """AutoencoderKLCogVideoX.encode on one frame (the reference-image path) against the reference's fp32 moments; the yardstick
+    is the oracle run in bf16 (the reference's own bf16 noise at this shape)."""
+    m, cfg, p, fx = enc
+    x = _img_tensor(fx["image"])
+    if mode == "tile":
+        x = x[:, :, :, :32, :48]
+    if mode == "tiled":
+        m.enable_slicing()
+        m.enable_tiling()
+    else:
+        m.disable_tiling()
+    with torch.no_grad():
+        got = m.encode(x.to(torch.bfloat16).to(dev)).latent_dist.parameters
+        pb = {k: v.to(torch.bfloat16) for k, v in p.items()}
+        floor_t = V.encode_moments(pb, cfg, x.to(torch.bfloat16), use_tiling=(mode == "tiled")).float()
+    torch.cuda.synchronize()
+    want = fx["moments_" + mode]
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    floor, err = rel(floor_t, want), rel(got, want)
+    print(f"vae encode[{mode}]: product {err:.3e}  reference-arithmetic-in-bf16 {floor:.3e}  (vs fp32 reference golden)")
+    assert err < max(1.5 * floor, 5e-3), (err, floor)
+
+
+def test_encode_reference_image_chain_and_errors(dev, enc):
+    """encode_reference_image (S/video_generate.py:26-38) with the fixture's noise draw reproduces the reference's
+    `ref_img_states`; multi-frame input is refused (no silent fallback); slicing over a batch equals per-sample encodes."""
+    import s2v_b200
+    m, cfg, p, fx = enc
+    m.enable_slicing()
+    m.enable_tiling()
+    gen = torch.Generator().manual_seed(63)
+    with torch.no_grad():
+        got = s2v_b200.encode_reference_image(m, fx["image"], generator=gen)
+    # the product draws its noise like the reference's randn_tensor does for bf16 parameters and a CPU generator (bf16 draw on the
+    # generator's device); the fixture's fp32 draw is a different stream, so the expectation is rebuilt from the reference's
+    # moments with the product's draw: sample = mean + std * noise, times scaling_factor, frames in front of channels
+    noise = torch.randn(fx["noise"].shape, generator=torch.Generator().manual_seed(63), dtype=torch.bfloat16).float()
+    want = (V.gaussian_sample(fx["moments_tiled"], noise) * cfg.scaling_factor).permute(0, 2, 1, 3, 4)
+    assert got.shape == want.shape == fx["ref_img_states"].shape
+    err = rel(got, want)
+    print(f"ref_img_states: {err:.3e}")
+    assert err < 2e-2
+    x = _img_tensor(fx["image"]).to(torch.bfloat16).to(dev)
+    with pytest.raises(NotImplementedError):
+        m.encode(torch.cat([x, x], dim=2))
+    with torch.no_grad():
+        two = m.encode(torch.cat([x, x.flip(3)])).latent_dist.parameters
+        assert torch.equal(two[:1], m.encode(x).latent_dist.parameters) and torch.equal(two[1:], m.encode(x.flip(3)).latent_dist.parameters)
+
+
+def test_encode_full_size_image_runs_and_is_deterministic(dev):
+    """480 x 720 reference image through the 5B VAE geometry (random weights), tiled as S/inference.py:206-207 sets it:
+    ref_img_states [1, 1, 16, 60, 90], finite, identical across two runs, and tile-consistent in the un-blended interior
+    (a tile's top-left rows/cols depend only on that tile)."""
+    import s2v_b200
+    cfg = V.VaeConfig()
+    p = {k: v.to(torch.bfloat16) for k, v in V.synth_encoder_params(cfg, seed=3).items()}
+    m = s2v_b200.AutoencoderKLCogVideoX(scaling_factor=0.7)
+    m.load_state_dict(p, strict=False)
+    m = m.to(torch.bfloat16).to(dev)
+    m.enable_slicing()
+    m.enable_tiling()
+    g = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (480, 720, 3), generator=g, dtype=torch.uint8).numpy()
+    with torch.no_grad():
+        a = s2v_b200.encode_reference_image(m, img, generator=torch.Generator().manual_seed(5))
+        b = s2v_b200.encode_reference_image(m, img, generator=torch.Generator().manual_seed(5))
+        x = _img_tensor(img).to(torch.bfloat16).to(dev)
+        mom = m.encode(x).latent_dist.parameters
+        tile00 = m._enc_engine().encode_call(m._encode_image(x[0]), 0, 0, 240, 360)
+    torch.cuda.synchronize()
+    assert a.shape == (1, 1, 16, 60, 90) and torch.isfinite(a.float()).all() and torch.equal(a, b)
+    assert mom.shape == (1, 32, 1, 60, 90)
+    assert torch.equal(mom[0, :, :, :25, :36], tile00[:, :, :25, :36])   # first tile, inside its crop limits, nothing blended into it
