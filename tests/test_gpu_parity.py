@@ -492,3 +492,50 @@ def test_fused_qkv_norm_rope_is_bit_identical_to_the_two_kernel_form(dev, B, S, 
     assert torch.equal(one[..., 2 * D:], plain[..., 2 * D:])          # v columns untouched
     assert not torch.equal(one[..., : 2 * D], plain[..., : 2 * D])    # q/k were transformed
     assert torch.equal(one, two), f"max diff {(one.float() - two.float()).abs().max().item()}"
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(120)
+def test_attention_survives_a_warpgroup_that_lags_many_tiles(dev):
+    """Regression for the issue-loop deadlock (hang under ncu's replay): delay the second query tile's softmax warpgroup by
+    100 us (~130 key tiles), so that chain 0 wants to run far ahead of chain 1.  The MMA-issuing thread bounds the run-ahead
+    to 3 tiles; the kernel must finish and return exactly what the default timing returns (the schedule changes, the
+    arithmetic does not).  Before the fix this configuration blocked the issuer on a K/V ring stage that only the lagging
+    chain's PV could release."""
+    from s2v_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(77)
+    B, S, H = 1, 19126, 2
+    qkv = torch.randn(B, S, 3 * H * 64, generator=g).to(BF16).to(dev)
+    base = torch.empty(B, S, H * 64, device=dev, dtype=BF16)
+    ops.attention(qkv, base, H)
+    lagged = torch.empty_like(base)
+    try:
+        assert lib.s2v_attn_set_skew_ns(100000) == 0
+        ops.attention(qkv, lagged, H)
+        torch.cuda.synchronize()
+    finally:
+        lib.s2v_attn_set_skew_ns(200)
+    assert torch.equal(base, lagged)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,S,H,boost_at", [(1, 1, 1, None), (1, 63, 1, None), (1, 65, 2, None), (1, 257, 1, None), (1, 700, 2, 300),
+                                            (2, 1500, 2, 1111), (1, 1500, 1, 64), (1, 1500, 1, 1400)])
+def test_attention_edge_sizes_and_moving_reference_max(dev, B, S, H, boost_at):
+    """Ragged sizes around the 64-key tile / 256-row CTA, and late keys whose scores exceed the first tile's maximum by far more
+    than the 2^64 window (exact-max path + O / l rescale in TMEM, including in the last two tiles), against torch SDPA in fp32."""
+    from s2v_b200 import ops
+    g = torch.Generator().manual_seed(1000 + S)
+    qkv = torch.randn(B, S, 3 * H * 64, generator=g)
+    if boost_at is not None:
+        qkv[:, boost_at:boost_at + 3, H * 64:2 * H * 64] *= 40.0     # a few keys with huge |k|: scores up to ~ +-2000
+        qkv[:, boost_at + 90:boost_at + 91, H * 64:2 * H * 64] *= 90.0
+    qkv = qkv.to(BF16).to(dev)
+    out = torch.full((B, S, H * 64), float("nan"), device=dev, dtype=BF16)
+    ops.attention(qkv, out, H)
+    torch.cuda.synchronize()
+    q, k, v = [t.view(B, S, H, 64).transpose(1, 2).float() for t in qkv.chunk(3, dim=-1)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref)[0] < 2e-2
