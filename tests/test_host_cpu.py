@@ -189,3 +189,25 @@ def test_shard_plans():
     pe = torch.arange(8).view(8, 1, 1).float()  # [neg0..3, pos0..3]
     assert parallel.select_prompt_embeds(pe, 4, parallel.plan(4, 2, 1)).flatten().tolist() == [1, 3, 5, 7]
     assert parallel.select_prompt_embeds(pe, 4, parallel.plan(4, 8, 5)).flatten().tolist() == [6]
+
+
+def test_vae_state_dict_halves_load_strictly_and_full_checkpoint_schema():
+    """AutoencoderKLCogVideoX keeps the reference's state-dict schema for BOTH halves; a decoder-only (or encoder-only) dict
+    loads that half strictly, a dict with a hole raises (autoencoder_kl_cogvideox.py:1020-1115 parameter tree)."""
+    import s2v_b200
+    from oracle import vae_oracle as V
+    cfg = V.VaeConfig(block_out_channels=(64, 64, 64, 64), layers_per_block=1, sample_height=64, sample_width=96)
+    m = s2v_b200.AutoencoderKLCogVideoX(block_out_channels=cfg.block_out_channels, layers_per_block=1, sample_height=64, sample_width=96)
+    dec, enc = V.synth_decoder_params(cfg, 1), V.synth_encoder_params(cfg, 2)
+    assert set(m.state_dict()) == set(dec) | set(enc)
+    r = m.load_state_dict(dec)
+    assert all(k.startswith("encoder.") for k in r.missing_keys) and not r.unexpected_keys
+    r = m.load_state_dict(enc)
+    assert all(k.startswith("decoder.") for k in r.missing_keys) and not r.unexpected_keys
+    assert not m.load_state_dict({**dec, **enc}).missing_keys
+    holed = dict(dec)
+    holed.pop("decoder.conv_in.conv.weight")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(holed)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({**dec, "decoder.bogus.weight": dec["decoder.conv_in.conv.bias"]})
