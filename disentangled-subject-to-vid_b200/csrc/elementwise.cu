@@ -111,8 +111,11 @@ __device__ __forceinline__ void row_modulate_store(const RowRegs<MAXV>& r, int n
     }
 }
 
+// The row stays PACKED (bf16 pairs, MAXV uint4 per lane) and is unpacked on the fly by each pass: half the registers of an fp32
+// copy, so more rows are in flight per SM (the fp32 form ran at 0.49 of the HBM copy bandwidth with 16 warps per SM).  The
+// arithmetic (order of the sums, the two-pass variance, affine then modulation) is unchanged.
 template <int MAXV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MAXV <= 12 ? 3 : 2)
 adaln_modulate_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, const bf16* __restrict__ ln_w,
                       const bf16* __restrict__ ln_b, const float* __restrict__ mod, int mod_stride, int shift_off_text,
                       int scale_off_text, int shift_off_other, int scale_off_other, long long rows, int S, int D,
@@ -123,15 +126,68 @@ adaln_modulate_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, const 
     const int b = int(row / S);
     const int s = int(row - (long long)b * S);
     const int nvec = D / 8;
-    RowRegs<MAXV> r;
-    row_load<MAXV>(x + row * D, nvec, lane, r);
-    float mean, rstd;
-    row_stats<MAXV>(r, nvec, lane, D, eps, mean, rstd);
-    row_affine<MAXV>(r, nvec, lane, mean, rstd, ln_w, ln_b);
+    uint4 raw[MAXV];
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) raw[i] = (i * 32 + lane < nvec) ? __ldg(xr + i * 32 + lane) : make_uint4(0u, 0u, 0u, 0u);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        float f[8];
+        unpack8(raw[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += f[j];
+    }
+    const float mean = warp_sum(sum) / float(D);
+    // (the unpacked values must not be kept alive from one pass to the next — common-subexpression elimination would turn the
+    // packed row back into an fp32 copy: "launder" the registers between passes)
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) asm volatile("" : "+r"(raw[i].x), "+r"(raw[i].y), "+r"(raw[i].z), "+r"(raw[i].w));
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        if (i * 32 + lane < nvec) {
+            float f[8];
+            unpack8(raw[i], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = f[j] - mean;
+                q += d * d;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / float(D) + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) asm volatile("" : "+r"(raw[i].x), "+r"(raw[i].y), "+r"(raw[i].z), "+r"(raw[i].w));
     const float* m = mod + (long long)b * mod_stride;
     const bool text = s < text_len;
-    row_modulate_store<MAXV>(r, nvec, lane, m + (text ? shift_off_text : shift_off_other),
-                             m + (text ? scale_off_text : scale_off_other), out + row * D);
+    const float* shift = m + (text ? shift_off_text : shift_off_other);
+    const float* scale = m + (text ? scale_off_text : scale_off_other);
+    uint4* orow = reinterpret_cast<uint4*>(out + row * D);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = i * 32 + lane;
+        if (vi < nvec) {
+            float f[8], wf[8], bfv[8];
+            unpack8(raw[i], f);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(ln_w) + vi), wf);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(ln_b) + vi), bfv);
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * vi);
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * vi + 1);
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * vi);
+            const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * vi + 1);
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float y = (f[j] - mean) * rstd * wf[j] + bfv[j];
+                o[j] = y * (1.0f + sc[j]) + sh[j];
+            }
+            orow[vi] = pack8(o);
+        }
+        asm volatile("" ::: "memory");   // keep the parameter loads of later vectors from being hoisted (register pressure -> spills)
+    }
 }
 
 template <int MAXV>
