@@ -266,43 +266,71 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 gate = p.mod + (long long)b * p.mod_stride + (s < p.text_len ? p.gate_off_text : p.gate_off_other) + n0;
             }
             if (EPI == S2V_EPI_QKV_NORM_ROPE) {
-                // one 64-column head vector at a time (BN is a multiple of 64 and head boundaries are 64-aligned)
+                // A tile is entirely q heads, k heads or v columns (BN divides H*64).  q/k: pass 1 computes each head vector's
+                // LayerNorm statistics; pass 2 walks the tile in 16-column chunks so that the row's cos / sin (uncoalesced: one
+                // table row per thread) are read ONCE per tile instead of once per head vector — the first version of this
+                // epilogue cost the GEMM 11 % on those reads.  Same arithmetic as head_norm_rope / qk_norm_rope_kernel.
+                constexpr int NH = BN / 64;
                 const int sidx = row_ok ? row % p.rows_per_batch : 0;
                 const bool rope = p.rope_cos != nullptr && sidx >= p.text_len;
-                const float* cs = rope ? p.rope_cos + (long long)(sidx - p.text_len) * 64 : nullptr;
-                const float* sn = rope ? p.rope_sin + (long long)(sidx - p.text_len) * 64 : nullptr;
+                const float* cs = p.rope_cos + (long long)(rope ? sidx - p.text_len : 0) * 64;
+                const float* sn = p.rope_sin + (long long)(rope ? sidx - p.text_len : 0) * 64;
+                const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+                const bool qk_tile = n0 < p.qk_cols;
+                const bool is_q = n0 < (p.qk_cols >> 1);
+                const bf16* nw = is_q ? p.nq_w : p.nk_w;
+                const bf16* nb = is_q ? p.nq_b : p.nk_b;
+                float mean[NH], rstd[NH];
 #pragma unroll 1
-                for (int hv = 0; hv < BN / 64; ++hv) {
+                for (int hv = 0; hv < NH; ++hv) {
                     uint32_t v0[32], v1[32];
-                    tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + hv * 64, v0);
-                    tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + hv * 64 + 32, v1);
+                    tmem_ld32(trow + hv * 64, v0);
+                    tmem_ld32(trow + hv * 64 + 32, v1);
                     tmem_ld_wait();
                     const int col0 = n0 + hv * 64;
-                    if (row_ok && col0 < p.N) {
-                        float f[64];
+                    float f[64];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            f[j] = __uint_as_float(v0[j]) * p.alpha;
-                            f[32 + j] = __uint_as_float(v1[j]) * p.alpha;
-                        }
-                        if (p.bias) {
+                    for (int j = 0; j < 32; ++j) {
+                        f[j] = __uint_as_float(v0[j]) * p.alpha;
+                        f[32 + j] = __uint_as_float(v1[j]) * p.alpha;
+                    }
+                    if (p.bias && col0 < p.N) {
 #pragma unroll
-                            for (int v8 = 0; v8 < 8; ++v8) {
-                                const uint4 bb = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + v8);
-                                const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+                        for (int v8 = 0; v8 < 8; ++v8) {
+                            const uint4 bb = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + v8);
+                            const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    f[v8 * 8 + 2 * j] += bf16_lo(bw[j]);
-                                    f[v8 * 8 + 2 * j + 1] += bf16_hi(bw[j]);
-                                }
+                            for (int j = 0; j < 4; ++j) {
+                                f[v8 * 8 + 2 * j] += bf16_lo(bw[j]);
+                                f[v8 * 8 + 2 * j + 1] += bf16_hi(bw[j]);
                             }
                         }
-                        if (col0 < p.qk_cols) {
+                    }
+                    if (qk_tile) {
 #pragma unroll
-                            for (int j = 0; j < 64; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));   // the projection output is bf16
-                            const bool is_q = col0 < (p.qk_cols >> 1);
-                            head_norm_rope(f, is_q ? p.nq_w : p.nk_w, is_q ? p.nq_b : p.nk_b, cs, sn, p.qk_eps);
+                        for (int j = 0; j < 64; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));   // the projection output is bf16
+                        float g[8];
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) {
+                            float a = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a += f[l * 8 + j];
+                            g[l] = a;
                         }
+                        const float m = (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) * (1.0f / 64.0f);
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) {
+                            float a = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float d = f[l * 8 + j] - m;
+                                a = fmaf(d, d, a);
+                            }
+                            g[l] = a;
+                        }
+                        mean[hv] = m;
+                        rstd[hv] = rsqrtf((((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]))) * (1.0f / 64.0f) + p.qk_eps);
+                    } else if (row_ok && col0 < p.N) {   // v columns: bias only
 #pragma unroll
                         for (int v8 = 0; v8 < 8; ++v8) {
                             uint4 o;
@@ -311,6 +339,78 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             o.z = pack_bf16x2(f[v8 * 8 + 4], f[v8 * 8 + 5]);
                             o.w = pack_bf16x2(f[v8 * 8 + 6], f[v8 * 8 + 7]);
                             *reinterpret_cast<uint4*>(orow + hv * 64 + v8 * 8) = o;
+                        }
+                    }
+                }
+                if (qk_tile) {
+#pragma unroll 1
+                    for (int c16 = 0; c16 < 4; ++c16) {
+                        float cc[16], ss[16], wf[16], bfv[16];
+                        if (rope) {
+#pragma unroll
+                            for (int v4 = 0; v4 < 4; ++v4) {
+                                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs) + c16 * 4 + v4);
+                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn) + c16 * 4 + v4);
+                                cc[v4 * 4] = c4.x; cc[v4 * 4 + 1] = c4.y; cc[v4 * 4 + 2] = c4.z; cc[v4 * 4 + 3] = c4.w;
+                                ss[v4 * 4] = s4.x; ss[v4 * 4 + 1] = s4.y; ss[v4 * 4 + 2] = s4.z; ss[v4 * 4 + 3] = s4.w;
+                            }
+                        }
+#pragma unroll
+                        for (int v8 = 0; v8 < 2; ++v8) {
+                            const uint4 wu = __ldg(reinterpret_cast<const uint4*>(nw) + c16 * 2 + v8);
+                            const uint4 bu = __ldg(reinterpret_cast<const uint4*>(nb) + c16 * 2 + v8);
+                            const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                wf[v8 * 8 + 2 * j] = bf16_lo(ww[j]); wf[v8 * 8 + 2 * j + 1] = bf16_hi(ww[j]);
+                                bfv[v8 * 8 + 2 * j] = bf16_lo(bw[j]); bfv[v8 * 8 + 2 * j + 1] = bf16_hi(bw[j]);
+                            }
+                        }
+#pragma unroll 1
+                        for (int hv = 0; hv < NH; ++hv) {
+                            uint32_t v[16];
+                            tmem_ld16(trow + hv * 64 + c16 * 16, v);
+                            tmem_ld_wait();
+                            const int col0 = n0 + hv * 64 + c16 * 16;
+                            if (!(row_ok && col0 < p.N)) continue;
+                            float f[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+                            if (p.bias) {
+#pragma unroll
+                                for (int v8 = 0; v8 < 2; ++v8) {
+                                    const uint4 bb = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + v8);
+                                    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        f[v8 * 8 + 2 * j] += bf16_lo(bw[j]);
+                                        f[v8 * 8 + 2 * j + 1] += bf16_hi(bw[j]);
+                                    }
+                                }
+                            }
+                            const float m = mean[hv], r = rstd[hv];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float xb = __bfloat162float(__float2bfloat16(f[j]));
+                                f[j] = fmaf((xb - m) * r, wf[j], bfv[j]);
+                            }
+                            if (rope) {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 2) {
+                                    const float x0 = __bfloat162float(__float2bfloat16(f[j])), x1 = __bfloat162float(__float2bfloat16(f[j + 1]));
+                                    f[j] = fmaf(x0, cc[j], -(x1 * ss[j]));
+                                    f[j + 1] = fmaf(x1, cc[j + 1], x0 * ss[j + 1]);
+                                }
+                            }
+#pragma unroll
+                            for (int v8 = 0; v8 < 2; ++v8) {
+                                uint4 o;
+                                o.x = pack_bf16x2(f[v8 * 8 + 0], f[v8 * 8 + 1]);
+                                o.y = pack_bf16x2(f[v8 * 8 + 2], f[v8 * 8 + 3]);
+                                o.z = pack_bf16x2(f[v8 * 8 + 4], f[v8 * 8 + 5]);
+                                o.w = pack_bf16x2(f[v8 * 8 + 6], f[v8 * 8 + 7]);
+                                *reinterpret_cast<uint4*>(orow + hv * 64 + c16 * 16 + v8 * 8) = o;
+                            }
                         }
                     }
                 }
