@@ -162,7 +162,7 @@ struct FrameMap {
 // out[(t+2), hp, wp, :] = SiLU( ((x - mean_g) * rstd_g * gamma + beta) * Y + B ) on interior positions, 0 on the border ring;
 // Y | B = yb[(ts*hl + (h >> lsh))*wl + (w >> lsw), 0:C | C:2C]  (conv_y / conv_b evaluated at latent resolution: a 1x1x1
 // convolution commutes with nearest-neighbour upsampling, autoencoder_kl_cogvideox.py:173-187).
-__global__ void __launch_bounds__(256) spatialnorm_silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
+__global__ void __launch_bounds__(256, 3) spatialnorm_silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
                                                                const float* __restrict__ stats, const bf16* __restrict__ gamma,
                                                                const bf16* __restrict__ beta, const bf16* __restrict__ yb, FrameMap fm,
                                                                int T, int H, int W, int C, int G, int hl, int wl, int lsh, int lsw) {
