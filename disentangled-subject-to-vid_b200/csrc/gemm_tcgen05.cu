@@ -266,20 +266,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 gate = p.mod + (long long)b * p.mod_stride + (s < p.text_len ? p.gate_off_text : p.gate_off_other) + n0;
             }
             if (EPI == S2V_EPI_QKV_NORM_ROPE) {
-                // A tile is entirely q heads, k heads or v columns (BN divides H*64).  q/k: pass 1 computes each head vector's
-                // LayerNorm statistics; pass 2 walks the tile in 16-column chunks so that the row's cos / sin (uncoalesced: one
-                // table row per thread) are read ONCE per tile instead of once per head vector — the first version of this
-                // epilogue cost the GEMM 11 % on those reads.  Same arithmetic as head_norm_rope / qk_norm_rope_kernel.
+                // Head vectors are 64 columns; a tile may hold q, k and v heads (small models).  Pass 1 computes each q/k head
+                // vector's LayerNorm statistics (v head vectors are finished there); pass 2 walks the tile in 16-column chunks so
+                // that the row's cos / sin (uncoalesced: one table row per thread) are read ONCE per tile instead of once per head
+                // vector.  Same arithmetic as head_norm_rope / qk_norm_rope_kernel.
                 constexpr int NH = BN / 64;
                 const int sidx = row_ok ? row % p.rows_per_batch : 0;
                 const bool rope = p.rope_cos != nullptr && sidx >= p.text_len;
                 const float* cs = p.rope_cos + (long long)(rope ? sidx - p.text_len : 0) * 64;
                 const float* sn = p.rope_sin + (long long)(rope ? sidx - p.text_len : 0) * 64;
                 const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-                const bool qk_tile = n0 < p.qk_cols;
-                const bool is_q = n0 < (p.qk_cols >> 1);
-                const bf16* nw = is_q ? p.nq_w : p.nk_w;
-                const bf16* nb = is_q ? p.nq_b : p.nk_b;
+                const bool qk_tile = n0 < p.qk_cols;   // at least the first head vector is a q or k head
                 float mean[NH], rstd[NH];
 #pragma unroll 1
                 for (int hv = 0; hv < NH; ++hv) {
@@ -306,7 +303,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             }
                         }
                     }
-                    if (qk_tile) {
+                    if (col0 < p.qk_cols) {
 #pragma unroll
                         for (int j = 0; j < 64; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));   // the projection output is bf16
                         float g[8];
@@ -345,7 +342,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (qk_tile) {
 #pragma unroll 1
                     for (int c16 = 0; c16 < 4; ++c16) {
-                        float cc[16], ss[16], wf[16], bfv[16];
+                        float cc[16], ss[16];
                         if (rope) {
 #pragma unroll
                             for (int v4 = 0; v4 < 4; ++v4) {
@@ -355,24 +352,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 ss[v4 * 4] = s4.x; ss[v4 * 4 + 1] = s4.y; ss[v4 * 4 + 2] = s4.z; ss[v4 * 4 + 3] = s4.w;
                             }
                         }
-#pragma unroll
-                        for (int v8 = 0; v8 < 2; ++v8) {
-                            const uint4 wu = __ldg(reinterpret_cast<const uint4*>(nw) + c16 * 2 + v8);
-                            const uint4 bu = __ldg(reinterpret_cast<const uint4*>(nb) + c16 * 2 + v8);
-                            const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                wf[v8 * 8 + 2 * j] = bf16_lo(ww[j]); wf[v8 * 8 + 2 * j + 1] = bf16_hi(ww[j]);
-                                bfv[v8 * 8 + 2 * j] = bf16_lo(bw[j]); bfv[v8 * 8 + 2 * j + 1] = bf16_hi(bw[j]);
-                            }
-                        }
 #pragma unroll 1
                         for (int hv = 0; hv < NH; ++hv) {
                             uint32_t v[16];
                             tmem_ld16(trow + hv * 64 + c16 * 16, v);
                             tmem_ld_wait();
                             const int col0 = n0 + hv * 64 + c16 * 16;
-                            if (!(row_ok && col0 < p.N)) continue;
+                            if (!(row_ok && col0 < p.qk_cols)) continue;   // v head vectors were stored by pass 1
+                            const bool is_q = col0 < (p.qk_cols >> 1);
+                            const bf16* nw = is_q ? p.nq_w : p.nk_w;
+                            const bf16* nb = is_q ? p.nq_b : p.nk_b;
+                            float wf[16], bfv[16];
+#pragma unroll
+                            for (int v8 = 0; v8 < 2; ++v8) {   // same address in every lane: one L1 wavefront each
+                                const uint4 wu = __ldg(reinterpret_cast<const uint4*>(nw) + c16 * 2 + v8);
+                                const uint4 bu = __ldg(reinterpret_cast<const uint4*>(nb) + c16 * 2 + v8);
+                                const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    wf[v8 * 8 + 2 * j] = bf16_lo(ww[j]); wf[v8 * 8 + 2 * j + 1] = bf16_hi(ww[j]);
+                                    bfv[v8 * 8 + 2 * j] = bf16_lo(bw[j]); bfv[v8 * 8 + 2 * j + 1] = bf16_hi(bw[j]);
+                                }
+                            }
                             float f[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;

@@ -274,12 +274,14 @@ def test_attention_processor_protocol(dev):
 
 
 # ---------------------------------------------------------------------------------------------- full-size properties
-def test_attention_full_size_properties(dev):
-    """cfg-3 sequence length (S = 19126, not a multiple of the 128-key tile): (1) V = const => output = const exactly up
-    to bf16 rounding (softmax rows sum to 1, masked tail keys contribute nothing); (2) linearity in V."""
+@pytest.mark.parametrize("S", [19126, 50626])
+def test_attention_full_size_properties(dev, S):
+    """cfg-3 (S = 19126) and cfg-4 / 720x1280 (S = 50626) sequence lengths, neither a multiple of the 64-key tile or the 256-row
+    CTA: (1) V = const => output = const exactly up to bf16 rounding (softmax rows sum to 1, masked tail keys contribute
+    nothing); (2) linearity in V; (3) torch SDPA in fp32 on the last 300 query rows (ragged tail included)."""
     from s2v_b200 import ops
     torch.manual_seed(0)
-    B, S, H = 1, 19126, 4
+    B, H = 1, (4 if S < 30000 else 2)
     qkv = torch.randn(B, S, 3 * H * 64, device=dev).to(BF16)
     qkv.view(B, S, 3, H, 64)[:, :, 2] = 0.75
     out = torch.empty(B, S, H * 64, device=dev, dtype=BF16)
@@ -461,7 +463,10 @@ def test_attach_reads_peft_layout_of_an_already_built_model(dev, golden_dir):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,S,H,L,lora,rope", [(2, 300, 2, 226, True, True), (1, 1000, 4, 226, False, True),
-                                                (2, 517, 6, 226, True, False), (1, 19126, 48, 226, True, True)])
+                                                (2, 517, 6, 226, True, False), (1, 19126, 48, 226, True, True),
+                                                (2, 300, 2, 226, False, True),     # 256-wide tiles holding q AND k heads
+                                                (1, 400, 3, 226, False, True),     # odd head count: q | k boundary inside a tile
+                                                (1, 290, 1, 226, False, False)])   # one tile holds q, k and v
 def test_fused_qkv_norm_rope_is_bit_identical_to_the_two_kernel_form(dev, B, S, H, L, lora, rope):
     """s2v_qkv_lora_norm_rope (LayerNorm(64)+RoPE in the GEMM epilogue) == s2v_qkv_lora followed by s2v_qk_norm_rope, bit for
     bit (D/models/attention_processor.py:2046-2076): same bf16 rounding of the projection, same reduction tree, same FMAs."""
