@@ -337,6 +337,22 @@ def test_c_abi_error_codes(dev):
     x = torch.zeros(8, 12, device=dev, dtype=BF16)  # K = 12 is not a multiple of 8
     a.x, a.w, a.out, a.M, a.N, a.K, a.ldx, a.ldw, a.ldo = x.data_ptr(), x.data_ptr(), x.data_ptr(), 8, 8, 12, 12, 12, 8
     assert lib.s2v_linear(C.byref(a), None) == -2
+    # entry points added for the fused QKV epilogue, the encoder and the frame conversion: bad arguments are refused with the
+    # library's negative codes (-1 bad argument, -2 unsupported shape), never a crash or a silent fallback
+    qk = _lib.QkNormArgs()
+    assert lib.s2v_qkv_lora_norm_rope(C.byref(a), C.byref(qk), None) == -1            # null norm weights
+    buf = torch.zeros(4096, device=dev, dtype=BF16)
+    qk.nq_w = qk.nq_b = qk.nk_w = qk.nk_b = buf.data_ptr()
+    qk.S, qk.H, qk.text_len, qk.eps = 8, 1, 0, 1e-6
+    a.K, a.ldx, a.ldw, a.N, a.ldo = 16, 16, 16, 128, 128                               # N must be 3 * H * 64
+    assert lib.s2v_qkv_lora_norm_rope(C.byref(a), C.byref(qk), None) == -1
+    assert lib.s2v_video_to_uint8(None, None, 1, 1, 4, 4, 0, None) == -1
+    assert lib.s2v_video_to_uint8(buf.data_ptr(), buf.data_ptr(), 1, 1, 3, 3, 0, None) == -2      # H*W % 4 != 0
+    assert lib.s2v_video_to_uint8(buf.data_ptr(), buf.data_ptr(), 1, 1, 4, 4, 2, None) == -1      # unknown rounding mode
+    assert lib.s2v_vae_subsample2(buf.data_ptr(), buf.data_ptr(), 1, 1, 8, 64, None) == -2        # H < 2
+    assert lib.s2v_vae_groupnorm_silu(buf.data_ptr(), buf.data_ptr(), None, buf.data_ptr(), buf.data_ptr(), 1, 4, 4, 64, 32, None) == -1
+    assert lib.s2v_vae_groupnorm_silu(buf.data_ptr(), buf.data_ptr(), buf.float().data_ptr(), buf.data_ptr(), buf.data_ptr(), 1, 4, 4, 60, 32,
+                                      None) == -2                                      # C % 8 != 0
 
 
 @pytest.mark.gpu
