@@ -257,6 +257,16 @@ def run_product(args, w):
                 "traffic": 925.2e6 if args.workload == "cfg3" else None, "algorithmic_bytes": 3 * S * D * 2 * 2 * P + S * D * 2 * 2 * P,
                 "peak_source": peak_src, "avg_launch_ms": round(attn["avg_ms"], 4),
                 "share_of_step": round(attn["total_ms"] / ms, 4)}
+        # the unit that actually bounds a head_dim-64 softmax: MUFU.EX2 issues 16 results / clk / SM (tools/microbench_mufu_mix.cu)
+        # against 8192 MMA flop / clk / SM, so one exponential per 256 MMA flop needs twice the cycles of its MMAs; the kernel
+        # sends 7 of 8 exponentials there.  Peak taken at the median SM clock sampled during the timed region.
+        sm_mhz = float((clocks or {}).get("sm_mhz") or 0)
+        if sm_mhz > 0:
+            exps = 2 * P * w["heads"] * float(S) * S * 7 / 8
+            xu_peak = 16 * 148 * sm_mhz * 1e6
+            roof["xu"] = {"mufu_ex2_per_s": round(exps / (attn["avg_ms"] / 1e3) / 1e12, 3), "peak_per_s": round(xu_peak / 1e12, 3),
+                          "unit": "T exp2/s", "frac": round(exps / (attn["avg_ms"] / 1e3) / xu_peak, 3),
+                          "tensor_frac_ceiling_if_xu_saturated": round(256 * xu_peak * 8 / 7 / 1e12 / peak_tf, 3)}
     gemm_fl = {"s2v_qkv_lora": 2 * S * D * (3 * D), "s2v_outproj_lora_gate_residual": 2 * S * D * D,
                "s2v_ffn_up_gelu_lora": 2 * S * D * 4 * D, "s2v_ffn_down_lora_gate_residual": 2 * S * D * 4 * D}
     kernels = {k: {"avg_ms": round(v["avg_ms"], 4), "share_of_step": round(v["total_ms"] / ms, 4),
