@@ -8,6 +8,7 @@
 // i+1.  Tiles are rasterised in groups of GROUP_M row-blocks so that one wave of 148 CTAs re-uses both the activation
 // panel and the weight panel out of the 126 MB L2.  The LoRA up-projection is folded in as extra K blocks read through
 // a second pair of tensor maps (no concatenated copies are materialised).
+#include <cstdlib>
 #include "common.cuh"
 #include "host_util.h"
 #include "s2v_b200.h"
@@ -44,6 +45,10 @@ struct GemmKParams {
 
 constexpr int S2V_EPI_CONV = 3;
 constexpr int S2V_EPI_QKV_NORM_ROPE = 4;
+// Convolution with the operands swapped (Cout = 128 layers): the weights [128, taps*Cin] are the M-side operand and 256
+// consecutive output positions the N-side one, D^T[cout, position].  A 128x128 tile reads 8 KB of shared memory per 64 tensor
+// cycles (the full 128 B/clk: the BN = 128 conv ran at 47 % tensor-pipe activity), a 128x256 tile 12 KB per 128.
+constexpr int S2V_EPI_CONV_T = 5;
 
 // Per-head LayerNorm(64) + interleaved RoPE on one head vector held by ONE thread, with exactly the arithmetic (operation
 // order, explicit FMAs, bf16 rounding points) of qk_norm_rope_kernel in elementwise.cu, so that the fused epilogue and the
@@ -134,10 +139,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
-    const int num_n = (p.N + BN - 1) / BN;
+    constexpr bool TR = (EPI == S2V_EPI_CONV_T);
+    constexpr int TILE_M = TR ? BN : GEMM_BM;          // problem rows (TR: output positions) per tile
+    const int num_m = (p.M + TILE_M - 1) / TILE_M;
+    const int num_n = TR ? 1 : (p.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
-    const int kb1 = (EPI == S2V_EPI_CONV) ? p.taps * p.cin_blocks : (p.K + GEMM_BK - 1) / GEMM_BK;
+    const int kb1 = (EPI == S2V_EPI_CONV || TR) ? p.taps * p.cin_blocks : (p.K + GEMM_BK - 1) / GEMM_BK;
     const int kb2 = (p.K2 + GEMM_BK - 1) / GEMM_BK;
     const int kb_total = kb1 + kb2;
 
@@ -172,14 +179,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int m_blk, n_blk;
                 tile_coords(tile, num_m, num_n, m_blk, n_blk);
-                const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+                const int m0 = m_blk * TILE_M, n0 = n_blk * BN;
                 const int lora_col0 = kb2 ? (n0 / p.lora_group_n) * p.K2 : 0;
                 for (int kb = 0; kb < kb_total; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    if (kb < kb1) {
+                    if (TR) {   // weights -> M-side slot (128 rows), 256 tap-shifted activation rows -> N-side slot
+                        const int tap = kb / p.cin_blocks;
+                        tma_load_2d(&tmB, &full_bar[stage], sa, kb * GEMM_BK, 0);
+                        tma_load_2d(&tmA, &full_bar[stage], sb, (kb - tap * p.cin_blocks) * GEMM_BK, p.a_row0 + m0 + p.tap_off[tap]);
+                    } else if (kb < kb1) {
                         if (EPI == S2V_EPI_CONV) {
                             const int tap = kb / p.cin_blocks;
                             tma_load_2d(&tmA, &full_bar[stage], sa, (kb - tap * p.cin_blocks) * GEMM_BK,
@@ -247,6 +258,58 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
+            if (TR) {
+                // lane = output channel, column = output position: 2-byte stores, 64 contiguous bytes per warp and position
+                const int ch = q * 32 + lane;
+                const bool ch_ok = ch < p.N;
+                const float bs = (p.bias && ch_ok) ? __bfloat162float(p.bias[ch]) : 0.f;
+                const int pos0 = m_blk * TILE_M;
+                const int rem = pos0 % (p.Hp * p.Wp);
+                int hp = rem / p.Wp, wp = rem - hp * p.Wp;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * 32, v);
+                    tmem_ld_wait();
+                    // the 32 residual values of the chunk are fetched first (read-only path, all in flight together): fetched
+                    // one by one between the stores they serialise — the compiler must assume out and res alias — and the
+                    // epilogue, not the MMAs, set the pace (250 instead of 1160 TFLOP/s)
+                    float rv[32];
+                    const int posc = pos0 + c * 32;
+                    if (p.res) {   // branch-free inside: clamped (always valid) addresses, so the 32 loads issue back to back
+                        const bf16* rp = p.res + (long long)p.out_row0 * p.ldres + (ch_ok ? ch : 0);
+                        unsigned short rraw[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            rraw[j] = __ldg(reinterpret_cast<const unsigned short*>(rp + (long long)min(posc + j, p.M - 1) * p.ldres));
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) rv[j] = __uint_as_float(uint32_t(rraw[j]) << 16);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) rv[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int pos = posc + j;
+                        const bool brd = (hp == 0) | (hp == p.Hp - 1) | (wp == 0) | (wp == p.Wp - 1);
+                        if (pos < p.M && ch_ok) {
+                            float f = __uint_as_float(v[j]) * p.alpha;
+                            f += bs;
+                            f += rv[j];
+                            if (brd) f = 0.f;
+                            p.out[(long long)(pos + p.out_row0) * p.ldo + ch] = __float2bfloat16(f);
+                        }
+                        if (++wp == p.Wp) {
+                            wp = 0;
+                            if (++hp == p.Hp) hp = 0;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                continue;
+            }
             const int row = m_blk * GEMM_BM + q * 32 + lane;
             const bool row_ok = row < p.M;
             const int n0 = n_blk * BN;
@@ -508,8 +571,9 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
     using Cfg = GemmCfg<BN>;
     CUtensorMap tmA, tmB, tmA2, tmB2;
     int rc;
-    if ((rc = make_tmap_2d_bf16(&tmA, a->x, conv ? conv->cin : a->K, conv ? conv->a_rows : a->M, a->ldx, GEMM_BK, GEMM_BM))) return rc;
-    if ((rc = make_tmap_2d_bf16(&tmB, a->w, a->K, a->N, a->ldw, GEMM_BK, BN))) return rc;
+    constexpr bool TR = (EPI == S2V_EPI_CONV_T);   // operands swapped: BN activation rows per box, 128 weight rows
+    if ((rc = make_tmap_2d_bf16(&tmA, a->x, conv ? conv->cin : a->K, conv ? conv->a_rows : a->M, a->ldx, GEMM_BK, TR ? BN : GEMM_BM))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tmB, a->w, a->K, a->N, a->ldw, GEMM_BK, TR ? GEMM_BM : BN))) return rc;
     const int K2 = a->lora_t ? a->lora_r : 0;
     if (K2) {
         const int groups = (a->N + a->lora_group_n - 1) / a->lora_group_n;
@@ -551,7 +615,7 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
         attr_done = true;
     }
-    const int num_tiles = ((a->M + GEMM_BM - 1) / GEMM_BM) * ((a->N + BN - 1) / BN);
+    const int num_tiles = TR ? (a->M + BN - 1) / BN : ((a->M + GEMM_BM - 1) / GEMM_BM) * ((a->N + BN - 1) / BN);
     const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
     return check_launch("gemm_tcgen05_kernel");
@@ -658,5 +722,10 @@ extern "C" int s2v_conv_gemm(const s2v_conv_args* c, void* stream_) {
     ConvExtra ex;
     ex.taps = c->taps; ex.cin = c->cin; ex.a_row0 = (int)(c->t_pad * plane); ex.out_row0 = (int)(c->t_pad * plane);
     ex.Hp = c->Hp; ex.Wp = c->Wp; ex.a_rows = (long long)(c->T + c->t_pad) * plane; ex.tap_off = off; ex.res = c->res; ex.ldres = c->ldres;
-    return (c->cout >= 256) ? launch_gemm<256, S2V_EPI_CONV>(&a, stream, &ex) : launch_gemm<128, S2V_EPI_CONV>(&a, stream, &ex);
+    if (c->cout >= 256) return launch_gemm<256, S2V_EPI_CONV>(&a, stream, &ex);
+    // Cout <= 128: one N block.  With at least 64 output channels and a 3x3(x3) kernel the swapped form (weights on the M side,
+    // 256 positions on the N side) halves the shared-memory operand traffic per flop; S2V_CONV_T=0 keeps the plain form (A/B).
+    static const bool conv_t = [] { const char* e = getenv("S2V_CONV_T"); return !(e && e[0] == '0'); }();
+    if (conv_t && c->cout >= 64 && c->cout <= 128 && c->taps > 1) return launch_gemm<256, S2V_EPI_CONV_T>(&a, stream, &ex);
+    return launch_gemm<128, S2V_EPI_CONV>(&a, stream, &ex);
 }
