@@ -723,9 +723,9 @@ extern "C" int s2v_conv_gemm(const s2v_conv_args* c, void* stream_) {
     ex.taps = c->taps; ex.cin = c->cin; ex.a_row0 = (int)(c->t_pad * plane); ex.out_row0 = (int)(c->t_pad * plane);
     ex.Hp = c->Hp; ex.Wp = c->Wp; ex.a_rows = (long long)(c->T + c->t_pad) * plane; ex.tap_off = off; ex.res = c->res; ex.ldres = c->ldres;
     if (c->cout >= 256) return launch_gemm<256, S2V_EPI_CONV>(&a, stream, &ex);
-    // Cout <= 128: one N block.  With at least 64 output channels and a 3x3(x3) kernel the swapped form (weights on the M side,
+    // Cout <= 128: one N block.  With a 3x3(x3) kernel the swapped form (weights on the M side,
     // 256 positions on the N side) halves the shared-memory operand traffic per flop; S2V_CONV_T=0 keeps the plain form (A/B).
     static const bool conv_t = [] { const char* e = getenv("S2V_CONV_T"); return !(e && e[0] == '0'); }();
-    if (conv_t && c->cout >= 64 && c->cout <= 128 && c->taps > 1) return launch_gemm<256, S2V_EPI_CONV_T>(&a, stream, &ex);
+    if (conv_t && c->cout <= 128 && c->taps > 1) return launch_gemm<256, S2V_EPI_CONV_T>(&a, stream, &ex);
     return launch_gemm<128, S2V_EPI_CONV>(&a, stream, &ex);
 }

@@ -36,7 +36,11 @@ for tiling in (True, False):
         torch.cuda.synchronize()
         l0 = s2v_b200._lib.launch_count
         t0 = time.time()
+        if it == 2 and tiling:
+            torch.cuda.nvtx.range_push("timed")   # `ncu --nvtx --nvtx-include "timed/"` captures one tiled decode
         out = vae.decode(z).sample
+        if it == 2 and tiling:
+            torch.cuda.nvtx.range_pop()
         torch.cuda.synchronize()
         ts.append(time.time() - t0)
         launches = s2v_b200._lib.launch_count - l0
