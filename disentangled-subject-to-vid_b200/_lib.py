@@ -89,7 +89,7 @@ SIGNATURES = {
     "s2v_vae_latent_rows": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_vae_latent_im2col": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_vae_groupnorm_stats": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
-    "s2v_vae_spatialnorm_silu": [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "s2v_vae_spatialnorm_silu": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(C.c_int32), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "s2v_vae_upsample_nearest": [_vp, _vp, C.POINTER(C.c_int32), _i32, _i32, _i32, _i32, _vp],
     "s2v_vae_volume_to_video": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "s2v_vae_groupnorm_silu": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],

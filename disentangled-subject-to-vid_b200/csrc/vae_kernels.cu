@@ -164,8 +164,8 @@ struct FrameMap {
 // convolution commutes with nearest-neighbour upsampling, autoencoder_kl_cogvideox.py:173-187).
 __global__ void __launch_bounds__(256, 3) spatialnorm_silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
                                                                const float* __restrict__ stats, const bf16* __restrict__ gamma,
-                                                               const bf16* __restrict__ beta, const bf16* __restrict__ yb, FrameMap fm,
-                                                               int T, int H, int W, int C, int G, int hl, int wl, int lsh, int lsw) {
+                                                               const bf16* __restrict__ beta, const bf16* __restrict__ yb, long long ldyb,
+                                                               FrameMap fm, int T, int H, int W, int C, int G, int hl, int wl, int lsh, int lsw) {
     // A block walks whole padded rows (t, hp); 256 % (C/8) == 0, so a thread always meets the same 8 channels and keeps their
     // GroupNorm scale / offset in registers; no per-element index division; four 16-byte loads in flight per thread.
     const int Hp = H + 2, Wp = W + 2, vpp = C >> 3, cpg = C / G;
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256, 3) spatialnorm_silu_kernel(const bf16* __
                 if (w >= W) break;
                 if (yb && (w >> lsw) != lcol) {
                     lcol = w >> lsw;
-                    const bf16* yr = yb + (lrow0 + lcol) * 2 * C + v * 8;
+                    const bf16* yr = yb + (lrow0 + lcol) * ldyb + v * 8;
                     v_unpack8(__ldg(reinterpret_cast<const uint4*>(yr)), yy);
                     v_unpack8(__ldg(reinterpret_cast<const uint4*>(yr + C)), bb);
                 }
@@ -408,11 +408,12 @@ extern "C" int s2v_vae_groupnorm_stats(const void* x, float* partial, float* sta
 }
 
 extern "C" int s2v_vae_spatialnorm_silu(const void* x, void* out, const float* stats, const void* gamma, const void* beta, const void* yb,
-                                        const int32_t* frame_src, int32_t T, int32_t H, int32_t W, int32_t C, int32_t G, int32_t hl,
-                                        int32_t wl, void* stream) {
+                                        int64_t ldyb, const int32_t* frame_src, int32_t T, int32_t H, int32_t W, int32_t C, int32_t G,
+                                        int32_t hl, int32_t wl, void* stream) {
     if (!x || !out || !stats || !gamma || !beta || !yb || !frame_src) return set_error(S2V_E_BADARG, "s2v_vae_spatialnorm_silu: null pointer");
     if (T <= 0 || T > 32 || (C % 8) || (C % G) || hl <= 0 || wl <= 0 || (H % hl) || (W % wl))
         return set_error(S2V_E_UNSUPPORTED, "s2v_vae_spatialnorm_silu: T <= 32, C % 8 == 0, H and W multiples of the latent size");
+    if (ldyb < 2 * C || (ldyb % 8)) return set_error(S2V_E_BADARG, "s2v_vae_spatialnorm_silu: ldyb must be >= 2*C and a multiple of 8");
     int lsh = 0, lsw = 0;
     while ((hl << lsh) < H) ++lsh;
     while ((wl << lsw) < W) ++lsw;
@@ -425,7 +426,7 @@ extern "C" int s2v_vae_spatialnorm_silu(const void* x, void* out, const float* s
     const int rows = T * (H + 2);
     spatialnorm_silu_kernel<<<rows < 148 * 8 ? rows : 148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16*>(x), static_cast<bf16*>(out), stats, static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta),
-        static_cast<const bf16*>(yb), fm, T, H, W, C, G, hl, wl, lsh, lsw);
+        static_cast<const bf16*>(yb), (long long)ldyb, fm, T, H, W, C, G, hl, wl, lsh, lsw);
     return check_launch("spatialnorm_silu_kernel");
 }
 
@@ -442,7 +443,7 @@ extern "C" int s2v_vae_groupnorm_silu(const void* x, void* out, const float* sta
     const int rows = T * (H + 2);
     spatialnorm_silu_kernel<<<rows < 148 * 8 ? rows : 148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16*>(x), static_cast<bf16*>(out), stats, static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta),
-        nullptr, fm, T, H, W, C, G, H, W, 0, 0);
+        nullptr, 0, fm, T, H, W, C, G, H, W, 0, 0);
     return check_launch("spatialnorm_silu_kernel");
 }
 

@@ -212,6 +212,7 @@ class _Conv:
 class _Norm:
     def __init__(self, gamma, beta, wyb, byb, C):
         self.gamma, self.beta, self.wyb, self.byb, self.C = gamma, beta, wyb, byb, C
+        self.yb_off = 0      # first column of this layer's conv_y | conv_b block in the engine's concatenated table
 
 
 class VaeDecoderEngine:
@@ -264,6 +265,16 @@ class VaeDecoderEngine:
                                 p[f"up_blocks.{b}.upsamplers.0.conv.bias"].contiguous(), w.shape[1], w.shape[0], 9)
         self._bufs: Dict[Tuple, torch.Tensor] = {}
         self._partial = torch.empty(GN_BLOCKS * max(self.ch) * 2, device=dev, dtype=torch.float32)
+        # conv_y | conv_b of EVERY SpatialNorm of a decoder call depend only on the latent rows: one GEMM over the concatenated
+        # weights produces all their tables (37 launch-bound 11 us GEMMs per call before); a layer reads its column slice
+        norms = [self.res[n][k] for n in names for k in ("norm1", "norm2")] + [self.norm_out]
+        off = 0
+        for nm in norms:
+            nm.yb_off = off
+            off += 2 * nm.C
+        self.yb_cols = off
+        self.yb_w = torch.cat([nm.wyb for nm in norms]).contiguous()
+        self.yb_b = torch.cat([nm.byb for nm in norms]).contiguous()
 
     # ---- packing
     def _conv3(self, name, im2col=False, pad_out=0) -> _Conv:
@@ -307,16 +318,15 @@ class VaeDecoderEngine:
         a.T, a.t_pad, a.Hp, a.Wp, a.cin, a.cout, a.taps = T, 2, H + 2, W + 2, cv.cin, cv.cout, cv.taps
         _call("s2v_conv_gemm", C.byref(a), _stream())
 
-    def _spatialnorm_silu(self, nm: _Norm, x: torch.Tensor, out: torch.Tensor, zrows: torch.Tensor, T: int, H: int, W: int, Tl: int,
+    def _spatialnorm_silu(self, nm: _Norm, x: torch.Tensor, out: torch.Tensor, yb_all: torch.Tensor, T: int, H: int, W: int, Tl: int,
                           hl: int, wl: int):
+        """yb_all [Tl*hl*wl, yb_cols]: conv_y | conv_b of every norm layer at latent resolution (decode_call)."""
         stats = torch.empty(self.G * 2, device=self.device, dtype=torch.float32)
         _call("s2v_vae_groupnorm_stats", x.data_ptr(), self._partial.data_ptr(), stats.data_ptr(), T, H, W, nm.C, self.G, GN_BLOCKS, 1e-6,
               _stream())
-        yb = torch.empty(zrows.shape[0], 2 * nm.C, device=self.device, dtype=BF16)
-        ops.linear(zrows, nm.wyb, nm.byb, yb)                                   # conv_y | conv_b at latent resolution
         src = (C.c_int32 * T)(*spatialnorm_frame_src(T, Tl))
         _call("s2v_vae_spatialnorm_silu", x.data_ptr(), out.data_ptr(), stats.data_ptr(), nm.gamma.data_ptr(), nm.beta.data_ptr(),
-              yb.data_ptr(), src, T, H, W, nm.C, self.G, hl, wl, _stream())
+              yb_all.data_ptr() + 2 * nm.yb_off, yb_all.shape[1], src, T, H, W, nm.C, self.G, hl, wl, _stream())
 
     @staticmethod
     def _context(key: str, U: torch.Tensor, T: int, cache: Dict[str, torch.Tensor], new_cache: Dict[str, torch.Tensor]):
@@ -361,6 +371,9 @@ class VaeDecoderEngine:
         new_cache: Dict[str, torch.Tensor] = {}
         zrows = torch.empty(Tl * hl * wl, self.ZK, device=self.device, dtype=BF16)
         _call("s2v_vae_latent_rows", z.data_ptr(), zrows.data_ptr(), Cz, Tz, hz, wz, f0, Tl, i0, j0, hl, wl, self.ZK, scale, _stream())
+        zrows_in = zrows
+        zrows = torch.empty(zrows_in.shape[0], self.yb_cols, device=self.device, dtype=BF16)     # every norm's conv_y | conv_b table
+        ops.linear(zrows_in, self.yb_w, self.yb_b, zrows)
         T, H, W = Tl, hl, wl
         col = self._vol("col", T, H, W, 27 * Cz)
         _call("s2v_vae_latent_im2col", z.data_ptr(), col[2:].data_ptr(), Cz, Tz, hz, wz, f0, Tl, i0, j0, hl, wl, scale, _stream())

@@ -226,13 +226,14 @@ S2V_API int s2v_vae_groupnorm_stats(const void* x, float* partial, float* stats,
                                     int32_t max_blocks, float eps, void* stream);
 
 /* out = SiLU( GroupNorm(x) * conv_y(zq') + conv_b(zq') ) written as a padded volume (border ring zero).  yb is the fused
- * conv_y|conv_b output at LATENT resolution [Tl*hl*wl, 2C]; frame_src[t] (host array, T <= 32) is the latent frame that
+ * conv_y|conv_b output at LATENT resolution: rows of [2C] values with row stride ldyb elements (ldyb > 2C when the tables of
+ * all norm layers of a decoder call come out of ONE GEMM and a layer reads its column slice); frame_src[t] (host array, T <= 32) is the latent frame that
  * nearest-neighbour interpolation assigns to output frame t (first frame kept separate when T is odd and > 1,
  * autoencoder_kl_cogvideox.py:173-181); H/hl and W/wl must be powers of two.
  * Replaces CogVideoXSpatialNorm3D.forward + the SiLU that follows it (:167-188, :297, :306, :974). */
 S2V_API int s2v_vae_spatialnorm_silu(const void* x, void* out, const float* stats, const void* gamma, const void* beta, const void* yb,
-                                     const int32_t* frame_src, int32_t T, int32_t H, int32_t W, int32_t C, int32_t G, int32_t hl,
-                                     int32_t wl, void* stream);
+                                     int64_t ldyb, const int32_t* frame_src, int32_t T, int32_t H, int32_t W, int32_t C, int32_t G,
+                                     int32_t hl, int32_t wl, void* stream);
 
 /* Nearest 2x upsampling in H and W with the temporal index map frame_src[t] (host array, T_out <= 32), written as the padded
  * input volume of the per-frame 3x3 conv.  The interpolate half of CogVideoXUpsample3D.forward (upsampling.py:385-405). */

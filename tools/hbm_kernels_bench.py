@@ -83,4 +83,4 @@ yb = torch.randn(3 * hl * wl, 2 * Cn, device=dev).to(BF16)
 src = (C.c_int32 * T)(*[min(t // 4, 2) for t in range(T)])
 report("vae spatialnorm_silu (read + write volume)", 2 * T * Hh * W * Cn * 2,
        timed(lambda: _lib.check(lib.s2v_vae_spatialnorm_silu(vol.data_ptr(), vout.data_ptr(), stats.data_ptr(), gam.data_ptr(), bet.data_ptr(), yb.data_ptr(),
-                                                             src, T, Hh, W, Cn, G, hl, wl, st()), "sn")))
+                                                             2 * Cn, src, T, Hh, W, Cn, G, hl, wl, st()), "sn")))

@@ -54,7 +54,7 @@ elif which == "spatialnorm":
     for _ in range(iters):
         _lib.check(lib.s2v_vae_groupnorm_stats(vol.data_ptr(), partial.data_ptr(), stats.data_ptr(), T, Hh, W, Cn, G, 1184, 1e-6, st), "gn")
         _lib.check(lib.s2v_vae_spatialnorm_silu(vol.data_ptr(), vout.data_ptr(), stats.data_ptr(), gam.data_ptr(), bet.data_ptr(), yb.data_ptr(),
-                                                src, T, Hh, W, Cn, G, hl, wl, st), "sn")
+                                                2 * Cn, src, T, Hh, W, Cn, G, hl, wl, st), "sn")
 elif which == "qkv_fused":
     M, H, L = B * S, 48, 226
     x = torch.randn(M, D, device=dev).to(torch.bfloat16)
