@@ -211,3 +211,28 @@ def test_vae_state_dict_halves_load_strictly_and_full_checkpoint_schema():
         m.load_state_dict(holed)
     with pytest.raises(RuntimeError):
         m.load_state_dict({**dec, "decoder.bogus.weight": dec["decoder.conv_in.conv.bias"]})
+
+
+def test_diagonal_gaussian_and_reference_image_input_checks():
+    """DiagonalGaussianDistribution follows D/models/autoencoders/vae.py:767-820 (chunk, clamp, std, sample = mean + std * noise with
+    the generator's draw, mode = mean); encode_reference_image refuses anything but an RGB uint8 image before touching the device."""
+    import numpy as np
+    import s2v_b200
+    from oracle import vae_oracle as V
+    from s2v_b200.vae import DiagonalGaussianDistribution
+    g = torch.Generator().manual_seed(5)
+    mom = torch.randn(2, 8, 1, 3, 4, generator=g) * 3
+    mom[0, 4, 0, 0, 0], mom[0, 5, 0, 0, 0] = 50.0, -50.0            # logvar beyond the clamp on both sides
+    d = DiagonalGaussianDistribution(mom)
+    assert torch.equal(d.mode(), mom[:, :4]) and float(d.logvar.max()) == 20.0 and float(d.logvar.min()) == -30.0
+    noise = torch.randn(d.mean.shape, generator=torch.Generator().manual_seed(9), dtype=mom.dtype)
+    assert torch.equal(d.sample(torch.Generator().manual_seed(9)), V.gaussian_sample(mom, noise))
+    assert torch.equal(DiagonalGaussianDistribution(mom, deterministic=True).sample(torch.Generator().manual_seed(1)), mom[:, :4])
+
+    class _Vae(torch.nn.Module):   # never reached: the input checks come first
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+    for bad in (np.zeros((4, 4, 3), dtype=np.float32), np.zeros((4, 4), dtype=np.uint8), np.zeros((4, 4, 4), dtype=np.uint8)):
+        with pytest.raises(ValueError):
+            s2v_b200.encode_reference_image(_Vae(), bad)
