@@ -17,3 +17,14 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The C-ABI library is built in-tree (git-ignored); build it when a fresh checkout runs the tests before build()."""
+    import importlib
+
+    b = importlib.import_module("disentangled-subject-to-vid_b200._build")
+    if not os.path.exists(b.LIB_PATH):
+        b.build()
+    return b.LIB_PATH
