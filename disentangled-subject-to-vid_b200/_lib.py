@@ -70,10 +70,6 @@ SIGNATURES = {
     "s2v_ffn_up_gelu_lora": [C.POINTER(LinearArgs), _vp],
     "s2v_ffn_down_lora_gate_residual": [C.POINTER(LinearArgs), _vp],
     "s2v_attn_fwd": [_vp, _vp, _i32, _i32, _i32, _f32, _vp],
-    "s2v_attn_fwd_v4": [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp],
-    "s2v_attn_set_debug_counters": [_vp],
-    "s2v_attn_set_poly16": [_i32],
-    "s2v_attn_set_skew_ns": [_i32],
     "s2v_adaln_modulate": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_final_norm": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_qk_norm_rope": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],

@@ -18,11 +18,13 @@ namespace s2v {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_GROUP_M = 16;
+constexpr int GEMM_GROUP_M_DEFAULT = 16;
 constexpr int GEMM_THREADS = 192;
 
 struct GemmKParams {
     int M, N, K, K2;
+    int group_m;        // row-blocks per rasterisation group (see tile_coords)
+    unsigned long long pol_a, pol_b;   // L2 eviction priority of the activation / weight TMA loads (see pick_l2_policy)
     int lora_group_n;
     const bf16* bias;
     bf16* out;
@@ -111,12 +113,15 @@ struct GemmCfg {
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
-    const int per_group = GEMM_GROUP_M * num_n;
+// Tiles are walked group by group: a group is `group_m` consecutive row-blocks x ALL column-blocks, row-block fastest.  While a
+// group is in flight its activation panel (group_m x 128 rows x K) is re-read by every wave and should stay in L2, and the weight
+// matrix streams through once per group: DRAM reads ~ |X| + |W| * num_m / group_m (host side: pick_group_m).
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
+    const int per_group = group_m * num_n;
     const int g = tile / per_group;
     const int r = tile - g * per_group;
-    const int m_first = g * GEMM_GROUP_M;
-    const int gm = min(GEMM_GROUP_M, num_m - m_first);
+    const int m_first = g * group_m;
+    const int gm = min(group_m, num_m - m_first);
     m_blk = m_first + r % gm;
     n_blk = r / gm;
 }
@@ -178,7 +183,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int m_blk, n_blk;
-                tile_coords(tile, num_m, num_n, m_blk, n_blk);
+                tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
                 const int m0 = m_blk * TILE_M, n0 = n_blk * BN;
                 const int lora_col0 = kb2 ? (n0 / p.lora_group_n) * p.K2 : 0;
                 for (int kb = 0; kb < kb_total; ++kb) {
@@ -196,13 +201,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             tma_load_2d(&tmA, &full_bar[stage], sa, (kb - tap * p.cin_blocks) * GEMM_BK,
                                         p.a_row0 + m0 + p.tap_off[tap]);
                         } else {
-                            tma_load_2d(&tmA, &full_bar[stage], sa, kb * GEMM_BK, m0);
+                            tma_load_2d_hint(&tmA, &full_bar[stage], sa, kb * GEMM_BK, m0, p.pol_a);
                         }
-                        tma_load_2d(&tmB, &full_bar[stage], sb, kb * GEMM_BK, n0);
+                        tma_load_2d_hint(&tmB, &full_bar[stage], sb, kb * GEMM_BK, n0, p.pol_b);
                     } else {
                         const int kk = (kb - kb1) * GEMM_BK;
-                        tma_load_2d(&tmA2, &full_bar[stage], sa, lora_col0 + kk, m0);
-                        tma_load_2d(&tmB2, &full_bar[stage], sb, kk, n0);
+                        tma_load_2d_hint(&tmA2, &full_bar[stage], sa, lora_col0 + kk, m0, p.pol_a);
+                        tma_load_2d_hint(&tmB2, &full_bar[stage], sb, kk, n0, p.pol_b);
                     }
                     if (++stage == Cfg::STAGES) {
                         stage = 0;
@@ -253,7 +258,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             int m_blk, n_blk;
-            tile_coords(tile, num_m, num_n, m_blk, n_blk);
+            tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -566,6 +571,26 @@ struct ConvExtra {
     long long ldres;
 };
 
+// Rasterisation group height: the group's activation panel (group_m x 128 rows x K bf16) should stay L2-resident while the
+// weights stream past it (126 MB L2; measurements in profiles/r02_summary.md).  S2V_GEMM_GROUP_M overrides for measurements.
+static int pick_group_m(int M, int K) {
+    static const int forced = [] { const char* e = getenv("S2V_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
+    if (forced > 0) return forced;
+    (void)M; (void)K;
+    return GEMM_GROUP_M_DEFAULT;
+}
+
+// L2 eviction priority of the two operand streams.  Every rasterisation group re-reads the WHOLE weight matrix (19 - 57 - 76 MB
+// for the out / QKV / FFN projections of the 5B model) while the activations stream through once per group: with the default
+// policy the 0.5 - 1.4 GB of activations and outputs of a launch push the weights out of the 126 MB L2 between groups (measured:
+// FFN-down reads 3.8 GB from DRAM for 1.25 GB of operands, profiles/r02_summary.md).  Mode 1 marks the weight loads evict-last,
+// mode 2 additionally marks the activation loads evict-first.  S2V_GEMM_L2_HINT overrides for measurements.
+static void pick_l2_policy(unsigned long long* pol_a, unsigned long long* pol_b) {
+    static const int mode = [] { const char* e = getenv("S2V_GEMM_L2_HINT"); return e ? atoi(e) : 0; }();
+    *pol_a = mode == 2 ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+    *pol_b = mode >= 1 ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+}
+
 template <int BN, int EPI>
 static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const ConvExtra* conv = nullptr, const s2v_qk_norm_args* qk = nullptr) {
     using Cfg = GemmCfg<BN>;
@@ -585,6 +610,9 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
     }
     GemmKParams p;
     p.M = a->M; p.N = a->N; p.K = a->K; p.K2 = K2;
+    p.group_m = pick_group_m(a->M, a->K + K2);
+    pick_l2_policy(&p.pol_a, &p.pol_b);
+    if (conv) p.pol_a = p.pol_b = L2_EVICT_NORMAL;   // the activation volume is the re-read operand there (27 taps)
     p.lora_group_n = a->lora_group_n > 0 ? a->lora_group_n : a->N;
     p.bias = static_cast<const bf16*>(a->bias);
     p.out = static_cast<bf16*>(a->out);
@@ -609,12 +637,7 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
     }
 
     auto kern = gemm_tcgen05_kernel<BN, EPI>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
-        attr_done = true;
-    }
+    if ((rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, "cudaFuncSetAttribute(gemm)"))) return rc;
     const int num_tiles = TR ? (a->M + BN - 1) / BN : ((a->M + GEMM_BM - 1) / GEMM_BM) * ((a->N + BN - 1) / BN);
     const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);

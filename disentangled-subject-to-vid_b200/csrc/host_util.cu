@@ -3,6 +3,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "s2v_b200.h"
 
 namespace s2v {
@@ -56,6 +58,30 @@ int sm_count() {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || g_sm_count[dev] == 0) return 148;
     return g_sm_count[dev];
+}
+
+int ensure_smem_optin(const void* kernel, int bytes, const char* what) {
+    struct Entry { const void* k; unsigned long long devs; };
+    static Entry table[64];
+    static int n = 0;
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return set_error(S2V_E_NO_DEVICE, "no current CUDA device");
+    std::lock_guard<std::mutex> lock(mu);
+    Entry* e = nullptr;
+    for (int i = 0; i < n; ++i)
+        if (table[i].k == kernel) e = &table[i];
+    if (!e) {
+        if (n == 64) return set_error(S2V_E_DRIVER, "ensure_smem_optin: kernel table full");
+        e = &table[n++];
+        e->k = kernel;
+        e->devs = 0;
+    }
+    if (e->devs & (1ull << dev)) return 0;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (err != cudaSuccess) return set_cuda_error(err, what);
+    e->devs |= 1ull << dev;
+    return 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -11,6 +11,9 @@ int set_cuda_error(cudaError_t e, const char* where);       // returns (int)e (>
 int check_launch(const char* kernel_name);                  // cudaPeekAtLastError after a launch
 int ensure_device();                                        // 0 if the current device is sm_100, else S2V_E_NO_DEVICE
 int sm_count();                                             // multiprocessors of the current device (cached)
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  The attribute is per device (context), so the
+// "done" flag is kept per (kernel, device ordinal) — a process that drives several GPUs opts in on each of them.
+int ensure_smem_optin(const void* kernel, int bytes, const char* what);
 
 // 2D row-major bf16 tensor [rows, cols] with leading dimension `ld` (elements); box = {box_cols, box_rows},
 // 128-byte swizzle, zero fill out of bounds.

@@ -48,11 +48,28 @@ class PackedLinear:
         return 0 if self.bb is None else self.bb.shape[1]
 
 
+_FP16_WARNED = False
+
+
 def _bf16c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Parameter as the kernels read it: bf16, contiguous.  bf16 parameters are live views.  fp16 parameters — the reference
+    loads CogVideoX-2B with torch_dtype=float16 (S/inference.py:191,210) — are rounded to bf16 ONCE here (a packed copy, refreshed
+    by repack()): the engine's arithmetic is bf16 x bf16 -> fp32 throughout, so a 2B run differs from the reference's fp16 run by
+    bf16 rounding (8 instead of 11 significand bits; INTEGRATION.md §5 gives the measured deviation).  fp32 parameters are refused:
+    nobody asking for fp32 wants a silent drop to 8 bits."""
+    global _FP16_WARNED
     if t is None:
         return None
+    if t.dtype == torch.float16:
+        if not _FP16_WARNED:
+            import warnings
+            warnings.warn("s2v_b200: float16 parameters are converted to bfloat16 copies (the sm_100a kernels compute in bf16 with fp32 "
+                          "accumulation); outputs are returned in float16", stacklevel=3)
+            _FP16_WARNED = True
+        return t.detach().to(BF16).contiguous()
     if t.dtype != BF16:
-        raise RuntimeError(f"the B200 engine computes in bfloat16; got a {t.dtype} parameter (load the model with torch_dtype=bfloat16)")
+        raise RuntimeError(f"the B200 engine computes in bfloat16; got a {t.dtype} parameter (load the model with torch_dtype=bfloat16 "
+                           "or float16)")
     return t.detach().contiguous()
 
 
@@ -206,12 +223,13 @@ class BlockRunner:
                     epilogue=ops.EPI_GATE_RESIDUAL, mod=mod2, gate_off_text=5 * D, gate_off_other=2 * D, rows_per_batch=S, text_len=L)
 
 
-def modulation(pl: PackedLinear, silu_in: torch.Tensor, out: torch.Tensor, scratch: torch.Tensor):
-    """out[B,N] = W silu(emb) + b (+ s B (A silu(emb))) — the 6D (or 2D) AdaLN vectors, fp32."""
-    ops.small_linear(silu_in, pl.w, pl.b, out, act_in=1)
+def modulation(pl: PackedLinear, x_in: torch.Tensor, out: torch.Tensor, scratch: torch.Tensor, act_in: int = 1):
+    """out[B,N] = W f(x) + b (+ s B (A f(x))), fp32, f = SiLU when act_in = 1 — the 6D (or 2D) AdaLN vectors from the time
+    embedding, and the two time-embedding linears themselves (any of them may carry an unmerged LoRA adapter)."""
+    ops.small_linear(x_in, pl.w, pl.b, out, act_in=act_in)
     if pl.a is not None:
         u = scratch[:, : pl.a.shape[0]]
-        ops.small_linear(silu_in, pl.a, None, u, act_in=1)
+        ops.small_linear(x_in, pl.a, None, u, act_in=act_in)
         ops.small_linear(u, pl.bb, None, out, alpha=pl.scale, beta=1.0)
     return out
 
@@ -265,7 +283,7 @@ class TransformerEngine:
         self.ln_eps = float(m.norm_final.eps)
         self.ff_dim = self.blocks[0].ff1.w.shape[0]
         rs = [pl.a.shape[0] for b in self.blocks for pl in (b.qkv, b.out, b.ff1, b.ff2, b.norm1, b.norm2) if pl.a is not None]
-        rs += [pl.a.shape[0] for pl in (self.text_proj, self.patch_proj) if pl.a is not None]
+        rs += [pl.a.shape[0] for pl in (self.text_proj, self.patch_proj, self.t1, self.t2, self.no_lin, self.proj_out) if pl.a is not None]
         self.max_r = max(rs) if rs else 0
 
     def workspace(self, B: int, S: int) -> Workspace:
@@ -287,9 +305,10 @@ class TransformerEngine:
             self._freqs = ops.timestep_freqs(self.D, self.device, self.freq_shift)
         ops.timestep_sinusoid(t, self._freqs, sin)
         h1 = torch.empty(B, self.time_dim, device=self.device, dtype=torch.float32)
-        ops.small_linear(sin, self.t1.w, self.t1.b, h1)
+        scratch = torch.empty(B, max(self.max_r, 8), device=self.device, dtype=torch.float32)
+        modulation(self.t1, sin, h1, scratch, act_in=0)      # the reference's LoRA targets do not reach these two layers
         emb = torch.empty(B, self.t2.w.shape[0], device=self.device, dtype=torch.float32)
-        ops.small_linear(h1, self.t2.w, self.t2.b, emb, act_in=1)
+        modulation(self.t2, h1, emb, scratch, act_in=1)      # (S/inference.py:222), but another LoraConfig may
         return emb
 
     def _embed_rows(self, pl: PackedLinear, rows: torch.Tensor, ws: Workspace, dst_rows: List[torch.Tensor], per: int):
@@ -369,7 +388,7 @@ class TransformerEngine:
         ops.final_norm(ws.h, fn, self.nf_w, self.nf_b, self.no_w, self.no_b, mod_out, shift_off=0, scale_off=D,
                        row0=L + n_ref, eps=self.ln_eps)
         tok = torch.empty(B * Fr * n, self.proj_out.w.shape[0], device=dev, dtype=BF16)
-        ops.linear(fn.view(B * Fr * n, D), self.proj_out.w, self.proj_out.b, tok)
+        runner.linear(self.proj_out, fn.view(B * Fr * n, D), tok, ws)
         out = torch.empty(B, Fr, self.out_ch, H, W, device=dev, dtype=BF16)
         ops.unpatchify(tok.view(B * Fr, n, -1), out.view(B * Fr, self.out_ch, H, W), p)
         return out

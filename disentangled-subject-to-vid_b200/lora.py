@@ -59,6 +59,22 @@ def _matches(name: str, targets: Iterable[str]) -> bool:
     return any(name == t or name.endswith("." + t) for t in targets)
 
 
+def invalidate_packed(model: nn.Module):
+    """Drop every packed-weight snapshot that hangs off `model` (the engine concatenates q|k|v and the LoRA factors, so they are
+    copies): this package's `_engine` / `_pb` / `_ws` caches and, on a stock model bound with `attach()`, the bound engine is
+    re-packed.  Called by everything that changes weights or adapters."""
+    for m in model.modules():
+        if getattr(m, "_engine", None) is not None:
+            m._engine = None
+        if getattr(m, "_pb", None) is not None:
+            m._pb = None
+        if getattr(m, "_ws", None) is not None and not isinstance(m._ws, dict):
+            m._ws = None
+    eng = getattr(model, "_s2v_engine", None)
+    if eng is not None:
+        eng.repack()
+
+
 def inject_lora(model: nn.Module, r: int, alpha: float, targets: Iterable[str] = REFERENCE_TARGETS, adapter: str = "default"):
     """Wrap every nn.Linear / nn.Conv2d whose dotted name matches a target suffix (PEFT's matching rule)."""
     targets = list(targets)
@@ -71,26 +87,42 @@ def inject_lora(model: nn.Module, r: int, alpha: float, targets: Iterable[str] =
             parent[int(child)] = wrapped
         else:
             setattr(parent, child, wrapped)
+    invalidate_packed(model)
     return names
 
 
-def load_lora_state_dict(model: nn.Module, state: Dict[str, torch.Tensor], adapter: str = "default", prefix: str = "transformer."):
-    """Load a `pytorch_lora_weights_transformer.safetensors`-style dict: keys `transformer.<module>.lora_{A,B}.weight`
-    (README.md:70-75; S/inference.py:68-105 strips the prefix and converts to the PEFT key form)."""
+def load_lora_state_dict(model: nn.Module, state: Dict[str, torch.Tensor], adapter: str = "default", prefix: str = "transformer.",
+                         strict: bool = True):
+    """Load a `pytorch_lora_weights_transformer.safetensors`-style dict.  Accepted key forms (after stripping `prefix`):
+    `<module>.lora_{A,B}.weight` (the file format, README.md:70-75) and `<module>.lora_{A,B}.<adapter>.weight` (the PEFT form that
+    `convert_unet_state_dict_to_peft` + `set_peft_model_state_dict` produce, S/inference.py:94-100).  Like the reference loader,
+    unexpected keys are reported: with `strict` (default) any key that is not a LoRA factor of an adapted module, or an adapted
+    module left without both factors, raises — a checkpoint that silently loads nothing would run with B = 0 (no subject)."""
     own = dict(model.named_modules())
-    loaded = 0
+    loaded, unexpected = {}, []
     for k, v in state.items():
         k = k[len(prefix):] if k.startswith(prefix) else k
-        mod, _, leaf = k.rpartition(".")
-        base, _, ab = mod.rpartition(".")
-        if ab not in ("lora_A", "lora_B") or leaf != "weight":
+        parts = k.split(".")
+        if len(parts) >= 3 and parts[-1] == "weight" and parts[-2] in ("lora_A", "lora_B"):
+            base, ab, ad = ".".join(parts[:-2]), parts[-2], adapter
+        elif len(parts) >= 4 and parts[-1] == "weight" and parts[-3] in ("lora_A", "lora_B"):
+            base, ab, ad = ".".join(parts[:-3]), parts[-3], parts[-2]
+        else:
+            unexpected.append(k)
             continue
         layer = own.get(base)
-        if layer is None or not hasattr(layer, ab):
-            raise KeyError(f"LoRA key {k!r} does not match an adapted module")
-        getattr(layer, ab)[adapter].weight.data.copy_(v)
-        loaded += 1
-    return loaded
+        if layer is None or not hasattr(layer, ab) or ad not in getattr(layer, ab):
+            raise KeyError(f"LoRA key {k!r} does not match an adapted module (adapter {ad!r})")
+        getattr(layer, ab)[ad].weight.data.copy_(v)
+        loaded.setdefault(base, set()).add(ab)
+    adapted = [n for n, m in own.items() if hasattr(m, "lora_A") and hasattr(m, "base_layer")]
+    incomplete = [n for n in adapted if loaded.get(n, set()) != {"lora_A", "lora_B"}]
+    if strict and (unexpected or incomplete or not loaded):
+        raise KeyError(f"load_lora_state_dict: {len(loaded)} of {len(adapted)} adapted modules received both factors; "
+                       f"unexpected keys: {unexpected[:5]}{'...' if len(unexpected) > 5 else ''}; "
+                       f"modules without both factors: {incomplete[:5]}{'...' if len(incomplete) > 5 else ''}")
+    invalidate_packed(model)
+    return sum(len(v) for v in loaded.values())
 
 
 @dataclass

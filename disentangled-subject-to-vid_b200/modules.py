@@ -36,6 +36,23 @@ def _no_eager(name):
     return forward
 
 
+class _PackedCache:
+    """Mixin for modules that cache packed weights (`_pb`) and workspaces (`_ws`): anything that replaces parameter storage
+    (load_state_dict, .to() / .cuda() / .bfloat16() via _apply) drops the snapshots of the whole subtree."""
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        from .lora import invalidate_packed
+        invalidate_packed(self)
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        from .lora import invalidate_packed
+        invalidate_packed(self)
+        return out
+
+
 class CogVideoXLayerNormZero(nn.Module):
     def __init__(self, conditioning_dim: int, embedding_dim: int, elementwise_affine: bool = True, eps: float = 1e-5,
                  bias: bool = True):
@@ -121,7 +138,7 @@ class CogVideoXAttnProcessor2_0:
         return out[:, enc_len:], out[:, :enc_len]
 
 
-class Attention(nn.Module):
+class Attention(_PackedCache, nn.Module):
     def __init__(self, query_dim: int, dim_head: int = 64, heads: int = 8, qk_norm: Optional[str] = "layer_norm",
                  eps: float = 1e-6, bias: bool = True, out_bias: bool = True, dropout: float = 0.0, processor=None):
         super().__init__()
@@ -173,7 +190,7 @@ class Attention(nn.Module):
         return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states, attention_mask=attention_mask, **kw)
 
 
-class CogVideoXBlock(nn.Module):
+class CogVideoXBlock(_PackedCache, nn.Module):
     def __init__(self, dim: int, num_attention_heads: int, attention_head_dim: int, time_embed_dim: int, dropout: float = 0.0,
                  activation_fn: str = "gelu-approximate", attention_bias: bool = False, qk_norm: bool = True,
                  norm_elementwise_affine: bool = True, norm_eps: float = 1e-5, final_dropout: bool = True,
@@ -247,7 +264,7 @@ class TimestepEmbedding(nn.Module):
     forward = _no_eager("TimestepEmbedding")
 
 
-class CogVideoXTransformer3DModel(nn.Module):
+class CogVideoXTransformer3DModel(_PackedCache, nn.Module):
     """CogVideoX DiT with the subject-to-video reference-image stream.  Same constructor defaults / config fields as
     cogvideox_transformer_3d.py:252-280 (2B defaults); `for_5b()` / `for_2b()` give the published geometries."""
 
@@ -317,8 +334,10 @@ class CogVideoXTransformer3DModel(nn.Module):
         return self._engine
 
     def invalidate_engine(self):
-        """Call after changing weights or adapters (load_state_dict, inject_lora, .to(...))."""
-        self._engine = None
+        """Drop the packed-weight snapshots (engine, per-block / per-attention caches).  load_state_dict, .to()/.cuda()/.half(),
+        inject_lora and load_lora_state_dict call this themselves; call it by hand after writing into parameters directly."""
+        from .lora import invalidate_packed
+        invalidate_packed(self)
 
     def forward(self, hidden_states: torch.Tensor, ref_img_states: torch.Tensor, encoder_hidden_states: torch.Tensor,
                 timestep: Union[int, float, torch.LongTensor], timestep_cond: Optional[torch.Tensor] = None,
@@ -346,6 +365,8 @@ def transformer_forward(engine: TransformerEngine, hidden_states, ref_img_states
     if not torch.is_tensor(timestep):
         timestep = torch.tensor([timestep], dtype=torch.float32)
     out = engine.forward(hidden_states, ref_img_states, encoder_hidden_states, timestep, rope=rope, eval=eval)
+    if hidden_states.dtype == torch.float16:   # a float16 (CogVideoX-2B) caller gets its dtype back; the arithmetic was bf16
+        out = out.to(torch.float16)
     if not return_dict:
         return (out,)
     return Transformer2DModelOutput(sample=out)
@@ -364,4 +385,21 @@ def attach(model: nn.Module, merge_lora: bool = False) -> nn.Module:
 
     model.forward = forward
     model._s2v_engine = eng
+    # weights that change under the bound engine re-pack it: load_state_dict (post hook), .to()/.cuda() (instance-level _apply),
+    # inject_lora / load_lora_state_dict (lora.invalidate_packed); `model.s2v_repack()` is the manual hook (e.g. after peft's
+    # add_adapter / set_peft_model_state_dict, which write parameters without going through any of the above)
+    model.s2v_repack = eng.repack
+    model.register_load_state_dict_post_hook(lambda module, incompatible_keys: eng.repack())
+    cls_apply = model._apply
+
+    def _apply(fn, *a, **k):
+        out = cls_apply(fn, *a, **k)
+        eng.device = next(model.parameters()).device
+        eng._ws.clear()
+        eng._pos_cache.clear()
+        eng._freqs = None
+        eng.repack()
+        return out
+
+    model._apply = _apply
     return model

@@ -167,12 +167,6 @@ def qk_norm_args(nq_w, nq_b, nk_w, nk_b, cos: Optional[torch.Tensor], sin: Optio
     return q
 
 
-# which attention kernel `attention()` launches: "default" (8 softmax warps) or "v4" (16 softmax warps) — both are sm_100a
-# tcgen05 kernels of this library with the same contract; S2V_ATTN_VARIANT selects at import for A/B runs
-ATTN_VARIANT = os.environ.get("S2V_ATTN_VARIANT", "default")
-ATTN_V4_POLY16, ATTN_V4_SKEW_NS = 1, 200
-
-
 def attention(qkv: torch.Tensor, out: torch.Tensor, heads: int, scale: Optional[float] = None) -> torch.Tensor:
     """qkv [B,S,3*H*64] -> out [B,S,H*64] (joint bidirectional attention, head_dim 64)."""
     _chk_bf16(qkv, "qkv")
@@ -182,12 +176,8 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, heads: int, scale: Optional[
         raise RuntimeError("attention: expected contiguous qkv [B,S,3*H*64] and out [B,S,H*64]")
     lib = _lib.load()
     with _timed("s2v_attn_fwd"):
-        if ATTN_VARIANT == "v4":
-            _lib.check(lib.s2v_attn_fwd_v4(qkv.data_ptr(), out.data_ptr(), B, S, heads, scale if scale is not None else 0.125,
-                                           ATTN_V4_POLY16, ATTN_V4_SKEW_NS, _stream()), "s2v_attn_fwd_v4")
-        else:
-            _lib.check(lib.s2v_attn_fwd(qkv.data_ptr(), out.data_ptr(), B, S, heads, scale if scale is not None else 0.125, _stream()),
-                       "s2v_attn_fwd")
+        _lib.check(lib.s2v_attn_fwd(qkv.data_ptr(), out.data_ptr(), B, S, heads, scale if scale is not None else 0.125, _stream()),
+                   "s2v_attn_fwd")
     return out
 
 
@@ -241,9 +231,11 @@ def small_linear(x, w, bias, out, *, act_in: int = 0, alpha: float = 1.0, beta: 
     if w.shape[1] != K or tuple(out.shape) != (B, N) or x.stride(1) != 1 or out.stride(1) != 1 or w.stride(1) != 1:
         raise RuntimeError("small_linear: shape mismatch")
     lib = _lib.load()
-    _lib.check(lib.s2v_small_linear(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(),
-                                    out.stride(0), B, N, K, act_in, alpha, beta, int(round_bf16), _stream()),
-               "s2v_small_linear")
+    for b0 in range(0, B, 8):   # the kernel keeps up to 8 input rows in registers; larger batches (> 4 prompts x 2 CFG halves) go in groups
+        nb = min(8, B - b0)
+        _lib.check(lib.s2v_small_linear(x[b0:].data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), out[b0:].data_ptr(),
+                                        out.stride(0), nb, N, K, act_in, alpha, beta, int(round_bf16), _stream()),
+                   "s2v_small_linear")
     return out
 
 

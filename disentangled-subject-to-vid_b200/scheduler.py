@@ -216,6 +216,15 @@ class CogVideoXDPMScheduler(CogVideoXDDIMScheduler):
         """randn_tensor(sample.shape, generator, device, dtype) (D/utils/torch_utils.py:38-83): drawn on the generator's device."""
         if variance_noise is not None:
             return variance_noise.to(device=sample.device, dtype=sample.dtype).contiguous()
+        if isinstance(generator, (list, tuple)):   # one generator per batch element, like randn_tensor (:66-76)
+            if len(generator) == 1:
+                generator = generator[0]
+            elif len(generator) != sample.shape[0]:
+                raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an effective batch"
+                                 f" size of {sample.shape[0]}. Make sure the batch size matches the length of the generators.")
+            else:
+                rows = [torch.randn((1,) + tuple(sample.shape[1:]), generator=g, device=g.device, dtype=sample.dtype) for g in generator]
+                return torch.cat(rows, dim=0).to(sample.device).contiguous()
         gdev = generator.device if generator is not None else sample.device
         return torch.randn(sample.shape, generator=generator, device=gdev, dtype=sample.dtype).to(sample.device).contiguous()
 

@@ -89,19 +89,6 @@ S2V_API int s2v_linear(const s2v_linear_args* a, void* stream);
  * Replaces F.scaled_dot_product_attention + the two transposes at D/models/attention_processor.py:2056-2058,2083-2088.
  */
 S2V_API int s2v_attn_fwd(const void* qkv, void* o, int32_t B, int32_t S, int32_t H, float softmax_scale, void* stream);
-/* Tuning knob (process-wide, not thread-safe): how many of every 8 exponential PAIRS the softmax evaluates with the FMA-pipe
- * polynomial instead of MUFU.EX2 (0..8).  Every setting computes the same function to within 7.5e-5 relative error. */
-S2V_API int s2v_attn_set_poly16(int32_t pairs_of_8);
-/* Profiling aid: when set to a device buffer of two uint64, every s2v_attn_fwd launch adds its per-CTA SM cycle counts and
- * wall-clock nanoseconds to it (sum cycles / sum ns = the SM clock the kernel actually ran at).  NULL (default) disables. */
-S2V_API int s2v_attn_set_debug_counters(void* dev_u64x2);
-/* Variant of s2v_attn_fwd with 16 softmax warps (two threads per query row); same contract and results to rounding.  Kept
- * beside the default for in-process A/B measurement (tools/attn_sweep.py); poly16 in 0..2. */
-S2V_API int s2v_attn_fwd_v4(const void* qkv, void* o, int32_t B, int32_t S, int32_t H, float softmax_scale, int32_t poly16,
-                            int32_t skew_ns, void* stream);
-/* Tuning knob: delay (ns, 0..100000) before the second query tile's softmax warpgroup starts, to keep the two warpgroups out
- * of phase. */
-S2V_API int s2v_attn_set_skew_ns(int32_t ns);
 
 /* ------------------------------------------------------------------------------------------------ AdaLN-Zero
  * out[b,s,:] = LayerNorm_D(x[b,s,:]; w, bias, eps) * (1 + scale) + shift, where (shift, scale) come from the

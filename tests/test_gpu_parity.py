@@ -77,7 +77,7 @@ def _rope_small(O):
 
 
 @pytest.mark.parametrize("tag", ["lora_rope", "plain"])
-def test_block_tiny_vs_reference_golden(dev, golden_dir, tag):
+def test_block_tiny_vs_reference_golden(dev, golden_dir, parity, tag):
     import s2v_b200
     O = _O()
     fx = torch.load(os.path.join(golden_dir, "block_tiny.pt"))[tag]
@@ -103,25 +103,35 @@ def test_block_tiny_vs_reference_golden(dev, golden_dir, tag):
         e_mine, _ = rel_err(g, ex)
         e_ref, _ = rel_err(r16, ex)
         e_gold, _ = rel_err(g, fx["out"][key])
-        print(f"block_tiny[{tag}].{key}: product {e_mine:.2e}  reference-bf16 {e_ref:.2e}  vs fp32 golden {e_gold:.2e}")
-        assert e_mine <= max(2.0 * e_ref, 4e-3), key
-        assert e_gold <= 3e-2, key
+        parity.check(f"block_tiny[{tag}].{key}", e_mine, ref=e_ref, default=max(2.0 * e_ref, 4e-3),
+                     note="same bf16-rounded weights, fp32 oracle")
+        parity.check(f"block_tiny[{tag}].{key}.vs_fp32_golden", e_gold, ref=rel_err(r16, fx["out"][key])[0], default=3e-2,
+                     note="reference golden (fp32 weights): includes the bf16 rounding of the weights")
 
 
 @pytest.mark.parametrize("tag", ["2b_plain", "5b_lora_rope"])
-def test_block_cfg1_shape(dev, golden_dir, tag):
-    """BASELINE.json configs[0] at full width (D = 1920 / 3072), B = 2, text 226 + ref 64 + video 64 tokens."""
+def test_block_cfg1_shape(dev, golden_dir, parity, tag):
+    """BASELINE.json configs[0] at full width (D = 1920 / 3072), B = 2, text 226 + ref 64 + video 64 tokens — ALL columns.
+    The committed reference golden keeps every 16th column plus the sum over all of them (fixture size); the oracle in fp32 is
+    first pinned on those (it reproduces the reference there to 1e-5 and the full-tensor sums), then the product is compared
+    with the oracle on every column."""
     import s2v_b200
     O = _O()
     fx = torch.load(os.path.join(golden_dir, "block_cfg1.pt"))[tag]
     cfg = O.TransformerConfig(**fx["cfg"])
-    p16 = bf16_params(O.synth_params(cfg, seed=21))
+    p32 = O.synth_params(cfg, seed=21)
+    p16 = bf16_params(p32)
     g = torch.Generator().manual_seed(22)
     D = cfg.inner_dim
-    io = dict(vid=torch.randn(2, 64, D, generator=g), txt=torch.randn(2, 226, D, generator=g),
-              ref=torch.randn(2, 64, D, generator=g), temb=torch.randn(2, 512, generator=g))
-    io = {k: v.to(BF16) for k, v in io.items()}
+    io32 = dict(vid=torch.randn(2, 64, D, generator=g), txt=torch.randn(2, 226, D, generator=g),
+                ref=torch.randn(2, 64, D, generator=g), temb=torch.randn(2, 512, generator=g))
+    io = {k: v.to(BF16) for k, v in io32.items()}
     rv, rr = _rope_small(O) if cfg.use_rotary_positional_embeddings else (None, None)
+    # pin: oracle fp32 (fp32 weights, fp32 inputs) == reference golden on the stored columns and on the full-tensor sums
+    pinned = O.block_forward(p32, cfg, "transformer_blocks.0.", io32["vid"], io32["txt"], io32["temb"], io32["ref"], rv, rr)
+    for t, key in zip(pinned, ("vid", "txt", "ref")):
+        assert rel_err(t[..., ::16], fx["out"][key])[0] < 1e-5, key
+        assert abs(float(t.double().sum()) - fx["out_sum"][key]) <= 1e-4 * float(t.double().abs().sum()), key
     blk = s2v_b200.CogVideoXBlock(dim=D, num_attention_heads=cfg.num_attention_heads, attention_head_dim=64, time_embed_dim=512,
                                   attention_bias=True).to(BF16)
     if cfg.lora_rank:
@@ -131,17 +141,60 @@ def test_block_cfg1_shape(dev, golden_dir, tag):
     got = blk(io["vid"].to(dev), io["txt"].to(dev), io["temb"].to(dev), io["ref"].to(dev), image_rotary_emb=rv, embed_ref_img=True,
               ref_img_seq_start=226, ref_img_seq_end=290, position_delta=0, ref_image_rotary_emb=rr)
     ref16 = O.block_forward(p16, cfg, "transformer_blocks.0.", io["vid"], io["txt"], io["temb"], io["ref"], rv, rr)
-    for gt, r16, key in zip(got, ref16, ("vid", "txt", "ref")):
-        gold = fx["out"][key]
-        e_mine, _ = rel_err(gt[..., ::16], gold)
-        e_ref, _ = rel_err(r16[..., ::16], gold)
-        print(f"block_cfg1[{tag}].{key}: product {e_mine:.2e}  reference-bf16 {e_ref:.2e}")
-        assert e_mine <= max(2.0 * e_ref, 4e-3), key
+    exact = O.block_forward(up(p16), cfg, "transformer_blocks.0.", io["vid"].float(), io["txt"].float(), io["temb"].float(),
+                            io["ref"].float(), rv, rr)
+    for gt, r16, ex, key in zip(got, ref16, exact, ("vid", "txt", "ref")):
+        e_mine, m_mine = rel_err(gt, ex)
+        e_ref, m_ref = rel_err(r16, ex)
+        parity.check(f"block_cfg1[{tag}].{key}", e_mine, ref=e_ref, default=max(2.0 * e_ref, 4e-3), max_abs=m_mine,
+                     ref_max_abs=m_ref, note="all columns; same bf16-rounded weights, fp32 oracle")
+
+
+# ---------------------------------------------------------------------------------------------- block at the BASELINE shape
+@pytest.mark.parametrize("tag", ["5b_lora_rope_S19126", "2b_plain_S19126"])
+def test_block_full_shape_vs_oracle(dev, parity, tag):
+    """ONE CogVideoXBlock at the cfg-3 / cfg-2 sequence length (text 226 + reference 1350 + video 13 x 1350 = 19 126 tokens;
+    D = 3072, H = 48, LoRA r = 128, RoPE  /  D = 1920, H = 30, no LoRA, no RoPE), one sequence, against oracle.block_forward on
+    the host (D/models/transformers/cogvideox_transformer_3d.py:122-186, attention_processor.py:2024-2097): fp32 oracle on the
+    same bf16-rounded weights = the error of the kernels; the oracle executed in bf16 = the reference's own noise floor."""
+    import s2v_b200
+    O = _O()
+    five = tag.startswith("5b")
+    cfg = O.TransformerConfig(num_attention_heads=48 if five else 30, num_layers=1, use_rotary_positional_embeddings=five,
+                              lora_rank=128 if five else 0, lora_alpha=64.0 if five else 0.0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    p16 = bf16_params(O.synth_params(cfg, seed=41))
+    D, n, Fr, L = cfg.inner_dim, 1350, 13, 226
+    g = torch.Generator().manual_seed(42)
+    io = dict(vid=torch.randn(1, Fr * n, D, generator=g), txt=torch.randn(1, L, D, generator=g),
+              ref=torch.randn(1, n, D, generator=g), temb=torch.randn(1, 512, generator=g))
+    io = {k: v.to(BF16) for k, v in io.items()}
+    rv, rr = O.pipeline_rope_tables(480, 720, Fr) if five else (None, None)
+    blk = s2v_b200.CogVideoXBlock(dim=D, num_attention_heads=cfg.num_attention_heads, attention_head_dim=64, time_embed_dim=512,
+                                  attention_bias=True).to(BF16)
+    if cfg.lora_rank:
+        s2v_b200.inject_lora(blk, cfg.lora_rank, cfg.lora_alpha)
+    load_flat_params(blk, {k[len("transformer_blocks.0."):]: v for k, v in p16.items() if k.startswith("transformer_blocks.0.")})
+    blk = blk.to(dev)
+    got = blk(io["vid"].to(dev), io["txt"].to(dev), io["temb"].to(dev), io["ref"].to(dev), image_rotary_emb=rv, embed_ref_img=True,
+              ref_img_seq_start=L, ref_img_seq_end=L + n, position_delta=0, ref_image_rotary_emb=rr)
+    got = [t.cpu() for t in got]
+    with torch.no_grad():
+        ref16 = O.block_forward(p16, cfg, "transformer_blocks.0.", io["vid"], io["txt"], io["temb"], io["ref"], rv, rr)
+        exact = O.block_forward(up(p16), cfg, "transformer_blocks.0.", io["vid"].float(), io["txt"].float(), io["temb"].float(),
+                                io["ref"].float(), rv, rr)
+    for gt, r16, ex, key in zip(got, ref16, exact, ("vid", "txt", "ref")):
+        assert gt.shape == ex.shape and torch.isfinite(gt.float()).all()
+        e_mine, m_mine = rel_err(gt, ex)
+        e_ref, m_ref = rel_err(r16, ex)
+        parity.check(f"block_full[{tag}].{key}", e_mine, ref=e_ref, default=max(2.0 * e_ref, 4e-3), max_abs=m_mine,
+                     ref_max_abs=m_ref, out_rms=float(ex.float().pow(2).mean().sqrt()),
+                     note="S=19126, all rows and columns; same bf16-rounded weights, fp32 oracle")
 
 
 # ---------------------------------------------------------------------------------------------- whole transformer
 @pytest.mark.parametrize("tag", ["lora_rope", "plain_sincos"])
-def test_transformer_tiny_vs_reference_golden(dev, golden_dir, tag):
+def test_transformer_tiny_vs_reference_golden(dev, golden_dir, parity, tag):
     O = _O()
     fx = torch.load(os.path.join(golden_dir, "transformer_tiny.pt"))[tag]
     cfg = O.TransformerConfig(**fx["cfg"])
@@ -160,12 +213,13 @@ def test_transformer_tiny_vs_reference_golden(dev, golden_dir, tag):
     e_mine, _ = rel_err(got, exact)
     e_ref, _ = rel_err(ref16, exact)
     e_gold, _ = rel_err(got, fx["out"])
-    print(f"transformer_tiny[{tag}]: product {e_mine:.2e}  reference-bf16 {e_ref:.2e}  vs fp32 golden {e_gold:.2e}")
-    assert e_mine <= max(2.0 * e_ref, 5e-3)
-    assert e_gold <= 3e-2
+    parity.check(f"transformer_tiny[{tag}]", e_mine, ref=e_ref, default=max(2.0 * e_ref, 5e-3), max_abs=rel_err(got, exact)[1],
+                 ref_max_abs=rel_err(ref16, exact)[1], note="same bf16-rounded weights, fp32 oracle")
+    parity.check(f"transformer_tiny[{tag}].vs_fp32_golden", e_gold, ref=rel_err(ref16, fx["out"])[0], default=3e-2,
+                 note="reference golden (fp32 weights): includes the bf16 rounding of the weights")
 
 
-def test_merged_lora_matches_fused_lora(dev, golden_dir):
+def test_merged_lora_matches_fused_lora(dev, golden_dir, parity):
     O = _O()
     fx = torch.load(os.path.join(golden_dir, "transformer_tiny.pt"))["lora_rope"]
     cfg = O.TransformerConfig(**fx["cfg"])
@@ -179,12 +233,12 @@ def test_merged_lora_matches_fused_lora(dev, golden_dir):
         outs.append(m(io["hidden"].to(dev, BF16), io["ref"].to(dev, BF16), io["text"].to(dev, BF16), io["timestep"].to(dev),
                       image_rotary_emb=rv, ref_image_rotary_emb=rr, return_dict=False, eval=True)[0])
     e, _ = rel_err(outs[1], outs[0])
-    assert e < 2e-2
+    parity.check("merged_lora_vs_fused_lora", e, default=2e-2, note="W + s B A folded in fp32 vs factors kept (two bf16 roundings apart)")
 
 
 # ---------------------------------------------------------------------------------------------- the loop
 @pytest.mark.parametrize("tag,dyn", [("fp32", False), ("fp32_dyncfg", True)])
-def test_pipeline_loop_vs_reference_golden(dev, golden_dir, tag, dyn):
+def test_pipeline_loop_vs_reference_golden(dev, golden_dir, parity, tag, dyn):
     """CustomCogVideoXPipeline.__call__ (3 DDIM steps, CFG 6, 480x720, 2 latent frames, LoRA, RoPE) against the
     reference pipeline's fp32 output; yardstick = the reference pipeline's own bf16 run (fixture 'bf16')."""
     import s2v_b200
@@ -201,9 +255,9 @@ def test_pipeline_loop_vs_reference_golden(dev, golden_dir, tag, dyn):
     gold = fx["runs"][tag]
     e_mine, m_mine = rel_err(out, gold)
     e_ref, m_ref = rel_err(fx["runs"]["bf16"], fx["runs"]["fp32"])
-    print(f"pipe_loop[{tag}]: product rel {e_mine:.2e} max {m_mine:.2e}; reference bf16-vs-fp32 rel {e_ref:.2e} max {m_ref:.2e}")
     assert out.dtype == BF16 and out.shape == gold.shape
-    assert e_mine <= max(2.0 * e_ref, 1e-2)
+    parity.check(f"pipe_loop[{tag}]", e_mine, ref=e_ref, default=max(2.0 * e_ref, 1e-2), max_abs=m_mine, ref_max_abs=m_ref,
+                 note="3 guided DDIM steps vs the reference pipeline's fp32 latents; yardstick = the reference pipeline's own bf16 run")
 
 
 # ---------------------------------------------------------------------------------------------- scheduler: bit-exact
@@ -251,7 +305,7 @@ def test_cfg_ddim_kernel_bit_exact_vs_torch_cuda(dev):
 
 
 # ---------------------------------------------------------------------------------------------- attention processor API
-def test_attention_processor_protocol(dev):
+def test_attention_processor_protocol(dev, parity):
     import s2v_b200
     O = _O()
     torch.manual_seed(3)
@@ -269,13 +323,14 @@ def test_attention_processor_protocol(dev):
     p = {f"a.{k}": v.detach().float().cpu() for k, v in attn.state_dict().items()}
     cfg = O.TransformerConfig(num_attention_heads=H)
     ev, ee = O.joint_attention(p, cfg, "a", vid.float(), enc.float(), 226, 64, rv, rr)
-    assert rel_err(hv, ev)[0] < 1.5e-2 and rel_err(he, ee)[0] < 1.5e-2
+    parity.check("attention_processor.video", rel_err(hv, ev)[0], default=1.5e-2, note="fp32 oracle joint_attention, D=128")
+    parity.check("attention_processor.encoder", rel_err(he, ee)[0], default=1.5e-2, note="fp32 oracle joint_attention, D=128")
     assert hv.shape == (2, 64, D) and he.shape == (2, 290, D)
 
 
 # ---------------------------------------------------------------------------------------------- full-size properties
 @pytest.mark.parametrize("S", [19126, 50626])
-def test_attention_full_size_properties(dev, S):
+def test_attention_full_size_properties(dev, parity, S):
     """cfg-3 (S = 19126) and cfg-4 / 720x1280 (S = 50626) sequence lengths, neither a multiple of the 64-key tile or the 256-row
     CTA: (1) V = const => output = const exactly up to bf16 rounding (softmax rows sum to 1, masked tail keys contribute
     nothing); (2) linearity in V; (3) torch SDPA in fp32 on the last 300 query rows (ragged tail included)."""
@@ -300,10 +355,11 @@ def test_attention_full_size_properties(dev, S):
     # against torch SDPA in fp32 on a slice of query rows including the ragged tail
     q, k, v = [t.transpose(1, 2).float() for t in qkv.view(B, S, 3, H, 64).unbind(2)]
     ref = F.scaled_dot_product_attention(q[:, :, -300:], k, v)
-    assert rel_err(outs[2].view(B, S, H, 64).transpose(1, 2)[:, :, -300:], ref)[0] < 1e-2
+    parity.check(f"attention_full_size[S={S}].last300rows", rel_err(outs[2].view(B, S, H, 64).transpose(1, 2)[:, :, -300:], ref)[0],
+                 default=1e-2, note="torch SDPA fp32 on the same bf16 q,k,v")
 
 
-def test_linear_full_size_sampled_rows(dev):
+def test_linear_full_size_sampled_rows(dev, parity):
     """cfg-3 QKV projection shape with LoRA (M = 2*19126 rows, ragged last M tile): sampled rows vs fp32 matmul."""
     from s2v_b200 import ops
     torch.manual_seed(1)
@@ -323,7 +379,7 @@ def test_linear_full_size_sampled_rows(dev):
     ref = xs @ w.float().t() + b.float()
     for g in range(3):
         ref[:, g * 3072:(g + 1) * 3072] += ts[:, g * r:(g + 1) * r] @ bb[g * 3072:(g + 1) * 3072].float().t()
-    assert rel_err(out[idx], ref)[0] < 5e-3
+    parity.check("linear_full_size.qkv_lora.sampled_rows", rel_err(out[idx], ref)[0], default=5e-3, note="fp32 matmul on the same bf16 operands")
 
 
 def test_c_abi_error_codes(dev):
@@ -355,26 +411,45 @@ def test_c_abi_error_codes(dev):
                                       None) == -2                                      # C % 8 != 0
 
 
-@pytest.mark.gpu
-def test_attention_v4_variant_matches_default(dev):
-    """The 16-softmax-warp variant (two threads per query row, named-barrier agreement on reference-max moves) computes the
-    same function as the default kernel, including ragged sizes and rows whose maximum jumps by > 2^64."""
-    import torch.nn.functional as F
-    from s2v_b200 import _lib
-    lib = _lib.load()
+def _attn_exp():
+    """tools/bin/libattn_exp.so: the product's attention source compiled with -DS2V_ATTN_EXPERIMENT (measurement-only entry point
+    with the warp-numbering / K-V-multicast / start-skew parameters).  Built on demand; travels to the GPU box with the snapshot."""
+    import ctypes as C
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "bin", "libattn_exp.so")
+    if not os.path.exists(path):
+        spec = importlib.util.spec_from_file_location("build_attn_exp", os.path.join(os.path.dirname(path), "..", "build_attn_exp.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    lib = C.CDLL(path)
+    lib.s2v_attn_fwd_exp.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p]
+    lib.s2v_attn_fwd_exp.restype = C.c_int
+    return lib
+
+
+def test_attention_kernel_variants_match_shipped(dev):
+    """Every template combination of the attention kernel (warp numbering HI, K/V multicast across a 2-CTA cluster MC) computes the
+    same bits as the shipped entry point: the schedule changes, the arithmetic does not.  Sizes cover an odd number of 256-row
+    query blocks (MC pads the grid with a partner-only CTA), ragged tails and rows whose maximum jumps by > 2^64."""
+    from s2v_b200 import ops
+    exp = _attn_exp()
     torch.manual_seed(3)
-    for (B, S, H, boost) in [(1, 1, 1, None), (1, 65, 2, None), (2, 700, 2, 300), (1, 1500, 1, 64)]:
+    for (B, S, H, boost) in [(1, 1, 1, None), (1, 65, 2, None), (2, 700, 2, 300), (1, 1500, 1, 64), (1, 3000, 3, 2900)]:
         qkv = torch.randn(B, S, 3 * H * 64, device=dev)
         if boost is not None:
             qkv[:, boost:boost + 3, H * 64:2 * H * 64] *= 40.0
-        qkv = qkv.to(torch.bfloat16)
-        out = torch.full((B, S, H * 64), float("nan"), device=dev, dtype=torch.bfloat16)
-        _lib.check(lib.s2v_attn_fwd_v4(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, 1, 200, torch.cuda.current_stream().cuda_stream),
-                   "s2v_attn_fwd_v4")
-        q, k, v = [t.view(B, S, H, 64).transpose(1, 2).float() for t in qkv.chunk(3, dim=-1)]
-        ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
-        err = float((out.float() - ref).abs().max() / ref.abs().max())
-        assert err < 2e-2, (B, S, H, boost, err)
+        qkv = qkv.to(BF16)
+        base = torch.empty(B, S, H * 64, device=dev, dtype=BF16)
+        ops.attention(qkv, base, H)
+        for variant in (0, 1, 2, 3):
+            out = torch.full((B, S, H * 64), float("nan"), device=dev, dtype=BF16)
+            rc = exp.s2v_attn_fwd_exp(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, variant, 1, 200, None,
+                                      torch.cuda.current_stream().cuda_stream)
+            assert rc == 0, (variant, rc)
+            torch.cuda.synchronize()
+            assert torch.equal(out, base), (B, S, H, boost, variant)
 
 
 # ---------------------------------------------------------------------------------------------- DPM scheduler (§8f next row)
@@ -523,27 +598,25 @@ def test_attention_survives_a_warpgroup_that_lags_many_tiles(dev):
     to 3 tiles; the kernel must finish and return exactly what the default timing returns (the schedule changes, the
     arithmetic does not).  Before the fix this configuration blocked the issuer on a K/V ring stage that only the lagging
     chain's PV could release."""
-    from s2v_b200 import _lib, ops
-    lib = _lib.load()
+    from s2v_b200 import ops
+    exp = _attn_exp()
     g = torch.Generator().manual_seed(77)
     B, S, H = 1, 19126, 2
     qkv = torch.randn(B, S, 3 * H * 64, generator=g).to(BF16).to(dev)
     base = torch.empty(B, S, H * 64, device=dev, dtype=BF16)
     ops.attention(qkv, base, H)
-    lagged = torch.empty_like(base)
-    try:
-        assert lib.s2v_attn_set_skew_ns(100000) == 0
-        ops.attention(qkv, lagged, H)
+    for variant in (0, 1, 2, 3):   # the same source as the shipped kernel, with the start skew as a parameter
+        lagged = torch.empty_like(base)
+        assert exp.s2v_attn_fwd_exp(qkv.data_ptr(), lagged.data_ptr(), B, S, H, 0.125, variant, 1, 100000, None,
+                                    torch.cuda.current_stream().cuda_stream) == 0
         torch.cuda.synchronize()
-    finally:
-        lib.s2v_attn_set_skew_ns(200)
-    assert torch.equal(base, lagged)
+        assert torch.equal(base, lagged), variant
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,S,H,boost_at", [(1, 1, 1, None), (1, 63, 1, None), (1, 65, 2, None), (1, 257, 1, None), (1, 700, 2, 300),
                                             (2, 1500, 2, 1111), (1, 1500, 1, 64), (1, 1500, 1, 1400)])
-def test_attention_edge_sizes_and_moving_reference_max(dev, B, S, H, boost_at):
+def test_attention_edge_sizes_and_moving_reference_max(dev, parity, B, S, H, boost_at):
     """Ragged sizes around the 64-key tile / 256-row CTA, and late keys whose scores exceed the first tile's maximum by far more
     than the 2^64 window (exact-max path + O / l rescale in TMEM, including in the last two tiles), against torch SDPA in fp32."""
     from s2v_b200 import ops
@@ -559,4 +632,5 @@ def test_attention_edge_sizes_and_moving_reference_max(dev, B, S, H, boost_at):
     q, k, v = [t.view(B, S, H, 64).transpose(1, 2).float() for t in qkv.chunk(3, dim=-1)]
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
     assert torch.isfinite(out.float()).all()
-    assert rel_err(out, ref)[0] < 2e-2
+    parity.check(f"attention_edge[B={B},S={S},H={H},boost={boost_at}]", rel_err(out, ref)[0], default=2e-2,
+                 note="torch SDPA fp32 on the same bf16 q,k,v")

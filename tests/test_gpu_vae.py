@@ -45,7 +45,7 @@ def bf16_floor(cfg, p, z, tiling):
         return V.decode(pb, cfg, z.to(torch.bfloat16), use_tiling=tiling).float()
 
 
-def test_conv_gemm_matches_torch_conv3d(dev):
+def test_conv_gemm_matches_torch_conv3d(dev, parity):
     """The implicit-GEMM causal 3x3x3 convolution alone, incl. the temporal context frames and the zeroed border ring."""
     import ctypes as C
     from s2v_b200 import _lib
@@ -75,7 +75,7 @@ def test_conv_gemm_matches_torch_conv3d(dev):
     assert torch.all(got[:, 0] == 0) and torch.all(got[:, -1] == 0) and torch.all(got[:, :, 0] == 0) and torch.all(got[:, :, -1] == 0)
     want_cl = want[0].permute(1, 2, 3, 0) + res[2:, 1:-1, 1:-1].float().cpu()
     err = float((got[:, 1:-1, 1:-1] - want_cl).abs().max() / want_cl.abs().max())
-    assert err < 1e-2, err          # one bf16 rounding of the output
+    parity.check("conv_gemm.3x3x3.small", err, default=1e-2, metric="max_abs/max", note="one bf16 rounding of the output; fp32 conv3d on the same bf16 operands")
 
 
 def test_blend_bit_exact_vs_torch_cuda(dev, vae):
@@ -96,7 +96,7 @@ def test_blend_bit_exact_vs_torch_cuda(dev, vae):
 
 
 @pytest.mark.parametrize("tiling", [False, True])
-def test_decode_vs_reference_golden(dev, fix, vae, tiling):
+def test_decode_vs_reference_golden(dev, fix, vae, parity, tiling):
     m, cfg, p = vae
     z = fix["z"]
     if tiling:
@@ -111,11 +111,11 @@ def test_decode_vs_reference_golden(dev, fix, vae, tiling):
     assert got.shape == want.shape and got.dtype == torch.bfloat16
     floor = rel(bf16_floor(cfg, p, z, tiling), want)
     err = rel(got, want)
-    print(f"vae decode[tiling={tiling}]: product {err:.3e}  reference-arithmetic-in-bf16 {floor:.3e}  (vs fp32 reference golden)")
-    assert err < max(1.5 * floor, 5e-3), (err, floor)
+    parity.check(f"vae_decode[tiling={tiling}]", err, ref=floor, default=max(1.5 * floor, 5e-3),
+                 max_abs=float((got.float().cpu() - want).abs().max()), note="vs the reference's fp32 decode (golden); yardstick = oracle in bf16")
 
 
-def test_decode_batch_and_chain(dev, fix, vae):
+def test_decode_batch_and_chain(dev, fix, vae, parity):
     m, cfg, p = vae
     m.enable_slicing()
     m.enable_tiling()
@@ -130,10 +130,10 @@ def test_decode_batch_and_chain(dev, fix, vae):
     with torch.no_grad():
         y = m.decode(fix["z"][:, :, :, :4, :6].to(torch.bfloat16).to(dev)).sample
     want = torch.cat([fix["decoder_chain"]["y0"], fix["decoder_chain"]["y1"]], dim=2)
-    assert rel(y, want) < 1.5e-2
+    parity.check("vae_decoder_chain", rel(y, want), default=1.5e-2, note="decoder.forward call chain with conv caches vs reference golden")
 
 
-def test_full_pipeline_call_with_vae_vs_oracle(dev):
+def test_full_pipeline_call_with_vae_vs_oracle(dev, parity):
     """CustomCogVideoXPipeline.__call__ end to end on the GPU (3 guided steps -> decode_latents -> postprocess 'pt') against
     the CPU oracle chain (denoise_loop -> decode_latents), i.e. rows P, S, R, T, B, N, A, F, L, O and V in one call."""
     import s2v_b200
@@ -178,8 +178,9 @@ def test_full_pipeline_call_with_vae_vs_oracle(dev):
     want = (want[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)           # video_processor.py:89-113
     assert frames.shape[1:] == want.shape and frames.shape[0] == 1
     err = float((frames[0].float().cpu() - want).abs().mean())
-    print(f"full pipeline: mean abs pixel error vs fp32 CPU oracle {err:.3e} (pixels in [0, 1])")
-    assert err < 2e-2
+    mx = float((frames[0].float().cpu() - want).abs().max())
+    parity.check("full_pipeline.pixels", err, default=2e-2, metric="mean_abs_pixel", max_abs=mx,
+                 note="3 guided steps + VAE decode + postprocess vs the fp32 CPU oracle; pixels in [0, 1]")
 
 
 def test_conv_gemm_full_size_sampled_positions_and_linearity(dev):
@@ -355,7 +356,7 @@ def _img_tensor(img):
 
 
 @pytest.mark.parametrize("mode", ["tile", "untiled", "tiled"])
-def test_encode_vs_reference_golden(dev, enc, mode):
+def test_encode_vs_reference_golden(dev, enc, parity, mode):
     """AutoencoderKLCogVideoX.encode on one frame (the reference-image path) against the reference's fp32 moments; the yardstick
     is the oracle run in bf16 (the reference's own bf16 noise at this shape)."""
     m, cfg, p, fx = enc
@@ -375,11 +376,11 @@ def test_encode_vs_reference_golden(dev, enc, mode):
     want = fx["moments_" + mode]
     assert got.shape == want.shape and got.dtype == torch.bfloat16
     floor, err = rel(floor_t, want), rel(got, want)
-    print(f"vae encode[{mode}]: product {err:.3e}  reference-arithmetic-in-bf16 {floor:.3e}  (vs fp32 reference golden)")
-    assert err < max(1.5 * floor, 5e-3), (err, floor)
+    parity.check(f"vae_encode[{mode}]", err, ref=floor, default=max(1.5 * floor, 5e-3),
+                 note="vs the reference's fp32 encode (golden); yardstick = oracle in bf16")
 
 
-def test_encode_reference_image_chain_and_errors(dev, enc):
+def test_encode_reference_image_chain_and_errors(dev, enc, parity):
     """encode_reference_image (S/video_generate.py:26-38) with the fixture's noise draw reproduces the reference's
     `ref_img_states`; multi-frame input is refused (no silent fallback); slicing over a batch equals per-sample encodes."""
     import s2v_b200
@@ -396,8 +397,7 @@ def test_encode_reference_image_chain_and_errors(dev, enc):
     want = (V.gaussian_sample(fx["moments_tiled"], noise) * cfg.scaling_factor).permute(0, 2, 1, 3, 4)
     assert got.shape == want.shape == fx["ref_img_states"].shape
     err = rel(got, want)
-    print(f"ref_img_states: {err:.3e}")
-    assert err < 2e-2
+    parity.check("ref_img_states", err, default=2e-2, note="encode_reference_image vs reference moments + same noise draw")
     x = _img_tensor(fx["image"]).to(torch.bfloat16).to(dev)
     with pytest.raises(NotImplementedError):
         m.encode(torch.cat([x, x], dim=2))

@@ -142,8 +142,22 @@ def test_lora_injection_targets_and_packing():
     per_block = {"attn1.to_q", "attn1.to_k", "attn1.to_v", "attn1.to_out.0", "norm1.linear", "norm2.linear", "ff.net.0.proj", "ff.net.2"}
     want = {f"transformer_blocks.{i}.{s}" for i in range(2) for s in per_block} | {"patch_embed.proj", "patch_embed.text_proj"}
     assert set(names) == want  # proj_out, norm_out.linear, time_embedding.* are NOT matched
-    sd = {f"transformer.{n}.lora_B.weight": torch.randn_like(m.get_submodule(n).lora_B["default"].weight) for n in names}
-    assert lora.load_lora_state_dict(m, sd) == len(names)
+    sd = {f"transformer.{n}.lora_{ab}.weight": torch.randn_like(getattr(m.get_submodule(n), f"lora_{ab}")["default"].weight)
+          for n in names for ab in "AB"}
+    assert lora.load_lora_state_dict(m, sd) == 2 * len(names)
+    # the PEFT key form written by convert_unet_state_dict_to_peft (S/inference.py:94) loads too ...
+    peft_form = {k.replace(".weight", ".default.weight")[len("transformer."):]: v + 1 for k, v in sd.items()}
+    assert lora.load_lora_state_dict(m, peft_form) == 2 * len(names)
+    k0 = f"{names[0]}.lora_B.default.weight"
+    assert torch.equal(m.get_submodule(names[0]).lora_B["default"].weight, peft_form[k0])
+    # ... and a checkpoint that would load nothing, half of the factors, or foreign keys is an error, not a silent B = 0 run
+    with pytest.raises(KeyError):
+        lora.load_lora_state_dict(m, {})
+    with pytest.raises(KeyError):
+        lora.load_lora_state_dict(m, {k: v for k, v in sd.items() if "lora_B" in k})
+    with pytest.raises(KeyError):
+        lora.load_lora_state_dict(m, dict(sd, **{"transformer.proj_out.weight": torch.zeros(1)}))
+    assert lora.load_lora_state_dict(m, dict(sd, **{"transformer.proj_out.weight": torch.zeros(1)}), strict=False) == 2 * len(names)
     pb = engine.pack_block(m.transformer_blocks[0])
     D = 128
     assert pb.qkv.w.shape == (3 * D, D) and pb.qkv.a.shape == (24, D) and pb.qkv.bb.shape == (3 * D, 8) and pb.qkv.group_n == D
@@ -156,10 +170,45 @@ def test_lora_injection_targets_and_packing():
     assert pm.qkv.a is None and torch.equal(pm.qkv.w[:D], w.to(torch.bfloat16))
 
 
-def test_engine_rejects_non_bf16():
+def test_engine_dtype_policy():
+    """fp32 parameters are refused; fp16 ones (how S/inference.py:191,210 loads CogVideoX-2B) are packed as bf16 copies."""
     m = _tiny_model()
     with pytest.raises(RuntimeError, match="bfloat16"):
         engine.pack_block(m.transformer_blocks[0])
+    h = _tiny_model().half()
+    with pytest.warns(UserWarning, match="float16"):
+        engine._FP16_WARNED = False
+        pb = engine.pack_block(h.transformer_blocks[0])
+    assert pb.qkv.w.dtype == torch.bfloat16 and pb.ln1_w.dtype == torch.bfloat16
+    assert torch.equal(pb.out.w, h.transformer_blocks[0].attn1.to_out[0].weight.to(torch.bfloat16))
+
+
+def test_packed_snapshots_are_dropped_when_weights_change():
+    """the engine's q|k|v / LoRA concatenations are copies; load_state_dict, .to(), inject_lora and load_lora_state_dict
+    must drop them (here on CPU: the caches are plain attributes, no kernel runs)."""
+    m = _tiny_model().to(torch.bfloat16)
+    blk = m.transformer_blocks[0]
+    blk._pb = engine.pack_block(blk)
+    blk.attn1._pb = object()
+    m._engine = object()
+    m.load_state_dict(m.state_dict())
+    assert m._engine is None and blk._pb is None and blk.attn1._pb is None
+    blk._pb, m._engine = object(), object()
+    lora.inject_lora(m, r=8, alpha=4.0)
+    assert m._engine is None and blk._pb is None
+    blk._pb, m._engine = object(), object()
+    m.to(torch.bfloat16)
+    assert m._engine is None and blk._pb is None
+    # a stock model bound with attach() is re-packed through the same paths
+    calls = []
+
+    class FakeEngine:
+        def repack(self):
+            calls.append(1)
+
+    m._s2v_engine = FakeEngine()
+    lora.invalidate_packed(m)
+    assert calls == [1]
 
 
 # ------------------------------------------------------------------ pipeline input validation (reference error surface)

@@ -27,7 +27,6 @@ ref = (0.7 * torch.randn(1, 1, 16, 60, 90, generator=g)).to(torch.bfloat16).to(d
 rope = pipe.rotary_tables(480, 720, F, dev)
 img, rr = (rope[0][n:], rope[1][n:]), (rope[0][:n], rope[1][:n])
 model_in = torch.cat([lat, lat])
-lib = _lib.load()
 
 
 def run(steps):
@@ -45,39 +44,49 @@ def run(steps):
     return round(timer.summary()["s2v_attn_fwd"]["avg_ms"], 3), round(e0.elapsed_time(e1) / steps, 1)
 
 
+import ctypes as C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+exp = C.CDLL(os.path.join(ROOT, "tools", "bin", "libattn_exp.so"))   # python tools/build_attn_exp.py
+exp.s2v_attn_fwd_exp.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p]
+exp.s2v_attn_fwd_exp.restype = C.c_int
+dbg = torch.zeros(2, dtype=torch.int64, device=dev)
+CUR = [0, 1, 200]
+shipped_attention = ops.attention
+
+
+def exp_attention(qkv, out, heads, scale=None):
+    B, S_, _ = qkv.shape
+    with ops._timed("s2v_attn_fwd"):
+        rc = exp.s2v_attn_fwd_exp(qkv.data_ptr(), out.data_ptr(), B, S_, heads, 0.125 if scale is None else scale, CUR[0], CUR[1], CUR[2],
+                                  dbg.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, rc
+    return out
+
+
 configs = {}
-for a in sys.argv[1:]:
-    name, variant, poly, skew = (a.split(":") + ["default", "1", "200"])[:4] if a.count(":") == 0 else a.split(":")
-    configs[name] = (variant, int(poly), int(skew))
+for a in sys.argv[1:]:   # name=variant:poly:skew   (variant bit 0 = HI warp numbering, bit 1 = K/V multicast); "shipped" = the product entry
+    name, spec = a.split("=")
+    configs[name] = None if spec == "shipped" else tuple(int(x) for x in spec.split(":"))
 if not configs:
-    configs = {"default_p1_s200": ("default", 1, 200), "default_p0_s200": ("default", 0, 200), "default_p2_s200": ("default", 2, 200),
-               "default_p1_s0": ("default", 1, 0), "v4_p1_s0": ("v4", 1, 0)}
-dbg = torch.zeros(42, dtype=torch.int64, device=dev)
-lib.s2v_attn_set_debug_counters(dbg.data_ptr())
+    configs = {"shipped": None, "r1_lo": (0, 1, 200), "hi": (1, 1, 200), "mc": (2, 1, 200), "hi_mc": (3, 1, 200)}
+steps = int(os.environ.get("STEPS", "2"))
 run(2)  # warm up (clocks settle on the power cap)
 res = {k: [] for k in configs}
-for rep in range(2):
-    for k, (variant, poly, skew) in configs.items():
-        ops.ATTN_VARIANT = variant
-        ops.ATTN_V4_POLY16, ops.ATTN_V4_SKEW_NS = poly, skew
-        lib.s2v_attn_set_poly16(poly)
-        lib.s2v_attn_set_skew_ns(skew)
+for rep in range(int(os.environ.get("REPS", "2"))):
+    for k in (list(configs) if rep % 2 == 0 else list(configs)[::-1]):
+        c = configs[k]
+        if c is None:
+            ops.attention = shipped_attention
+        else:
+            CUR[:] = c
+            ops.attention = exp_attention
+        s2v_b200.engine.ops.attention = ops.attention
         dbg.zero_()
-        r = run(2)
-        c, ns = [int(x) for x in dbg.tolist()[:2]]
-        res[k].append(r + (round(c / max(ns, 1) * 1e3), round(c / (2 * 42 * 7200) / 299)))   # + (attention SM MHz, cycles per 64-key step)
+        r = run(steps)
+        cyc, ns = [int(x) for x in dbg.tolist()]
+        res[k].append(r + ((round(cyc / max(ns, 1) * 1e3), round(cyc / (steps * 42 * 7200) / 299)) if c is not None else ()))   # + (attention SM MHz, cycles per 64-key step)
+ops.attention = shipped_attention
 for k, v in res.items():
-    print(json.dumps({"config": k, "attn_ms, step_ms, attn_sm_mhz, cycles_per_step": v}))
-
-# the same kernel in isolation (sustained loop), for the clock / cycle comparison
-qkv = torch.randn(2, S, 3 * D, device=dev).to(torch.bfloat16)
-out = torch.empty(2, S, D, device=dev, dtype=torch.bfloat16)
-lib.s2v_attn_set_poly16(1); lib.s2v_attn_set_skew_ns(200); ops.ATTN_VARIANT = "default"
-for _ in range(20): ops.attention(qkv, out, w["heads"])
-torch.cuda.synchronize(); dbg.zero_()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(20): ops.attention(qkv, out, w["heads"])
-e1.record(); torch.cuda.synchronize()
-c, ns = [int(x) for x in dbg.tolist()[:2]]
-print(json.dumps({"isolated_sustained_attn_ms": round(e0.elapsed_time(e1) / 20, 3), "attn_sm_mhz": round(c / ns * 1e3), "cycles_per_step": round(c / (20 * 7200) / 299)}))
+    print(json.dumps({"config": k, "spec": configs[k], "attn_ms, step_ms, attn_sm_mhz, cycles_per_step": v}), flush=True)
