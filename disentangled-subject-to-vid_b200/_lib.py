@@ -112,6 +112,8 @@ def load() -> C.CDLL:
             fn.restype = C.c_int
         lib.s2v_last_error.argtypes = []
         lib.s2v_last_error.restype = C.c_char_p
+        lib.s2v_workspace_bytes.argtypes = [_i32] * 6
+        lib.s2v_workspace_bytes.restype = C.c_int64
         if lib.s2v_abi_version() != 1:
             raise RuntimeError("libs2v_b200.so ABI version mismatch")
         _lib = lib

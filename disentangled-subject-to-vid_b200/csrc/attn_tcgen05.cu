@@ -37,8 +37,8 @@
 //   * POLY of every 8 exponentials are evaluated on the FMA pipe (Cody-Waite split + degree-3 minimax, rel. error
 //     7.5e-5, far below the bf16 rounding of P) instead of MUFU.EX2.
 //
-// TMEM columns (512): Q0 0 | Q1 32 | (64 free) | S[0][0] 128 | S[0][1] 192 | S[1][0] 256 | S[1][1] 320 | O0 384 | O1 448;
-// P_q(t) (bf16) overwrites the first 32 columns of its own score buffer S[q][t&1] once the scores are in registers
+// TMEM columns (512): Q0 0 | Q1 32 | S[0][0] 64 | S[0][1] 64+BK | S[1][0] 64+2BK | S[1][1] 64+3BK | O0 384 | O1 448;
+// P_q(t) (bf16) overwrites the first BK/2 columns of its own score buffer S[q][t&1] once the scores are in registers
 //
 // Global layout: qkv [B, S, 3*H*64] (q|k|v, heads contiguous) read through ONE 4-D tensor map {64, 3H, S, B};
 // out [B, S, H*64].  Key rows >= S are zero-filled by TMA and masked to -inf; query rows >= S are not stored.
@@ -51,16 +51,18 @@ namespace s2v {
 constexpr int ATT_D = 64;
 constexpr int ATT_BQ = 128;         // rows per query tile (UMMA M)
 constexpr int ATT_QTILES = 2;       // query tiles per CTA
-constexpr int ATT_BK = 64;          // keys per tile
 constexpr int ATT_STAGES = 8;       // K/V ring depth
 constexpr int ATT_THREADS = 384;    // 12 warps
 constexpr int ATT_POLY16_DEFAULT = 1;  // of every 8 PAIRS (16 exponentials), how many pairs run on the FMA pipe
-constexpr uint32_t ATT_TILE_BYTES = ATT_BK * ATT_D * 2;  // 8 KB
-constexpr uint32_t ATT_SMEM_BYTES = 2 * ATT_STAGES * ATT_TILE_BYTES + 1024 + 256;
+// keys per tile BK (template parameter): 64, or 80 — the largest tile whose double-buffered fp32 scores still fit TMEM next to Q and O
+// (2 x 32 + 4 x 80 + 2 x 64 = 512 columns): 10 % fewer tcgen05.mma per key for the single issuing thread and 20 % fewer barrier
+// round trips per key for the softmax warps
+__host__ __device__ constexpr uint32_t att_tile_bytes(int bk) { return uint32_t(bk) * ATT_D * 2; }   // 8 / 10 KB
+__host__ __device__ constexpr uint32_t att_smem_bytes(int bk) { return 2 * ATT_STAGES * att_tile_bytes(bk) + 1024 + 256; }
 constexpr float ATT_P_LIMIT_LOG2 = 64.0f;     // probabilities are kept below 2^64 relative to the reference max
 constexpr float ATT_SUM_LIMIT = 1.8446744e19f;  // 2^64
 
-constexpr uint32_t TM_Q = 0, TM_S = 128, TM_O = 384;  // Q_q at q*32, S[q][b] at 128+q*128+b*64 (P(t) over its first 32 columns), O_q at 384+q*64
+constexpr uint32_t TM_Q = 0, TM_S = 64, TM_O = 384;  // Q_q at q*32, S[q][b] at 64+(2q+b)*BK (P(t) over its first BK/2 columns), O_q at 384+q*64
 
 __device__ __forceinline__ uint64_t pack2(float a, float b) {
     uint64_t r;
@@ -107,11 +109,14 @@ __device__ __forceinline__ void exp2_poly2(uint64_t X, float& r0, float& r1, flo
     r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-template <int POLY16, bool HI, bool MC>
+template <int BK, int POLY16, bool HI, bool MC>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H,
                 float scale_log2, int skew_ns, unsigned long long* __restrict__ dbg) {
     constexpr int W_TMA = HI ? 8 : 0, W_MMA = HI ? 9 : 1, W_SOFT0 = HI ? 0 : 4;   // warp roles (see the header comment)
+    constexpr int ATT_BK = BK;
+    constexpr uint32_t ATT_TILE_BYTES = att_tile_bytes(BK);
+    static_assert(BK % 16 == 0 && TM_S + 4 * BK <= TM_O, "score buffers must fit between Q and O");
     extern __shared__ uint8_t smem_raw[];
     unsigned long long dbg_c0 = 0, dbg_t0 = 0;
     if (dbg && threadIdx.x == 0) {
@@ -198,15 +203,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + stage * ATT_TILE_BYTES), 16, 1024);
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)
-                    umma_ts(tmem_base + TM_S + q * 128 + buf * 64, tmem_base + TM_Q + q * 32 + k * 8, bdesc + uint64_t(k * 2),
+                    umma_ts(tmem_base + TM_S + (q * 2 + buf) * BK, tmem_base + TM_Q + q * 32 + k * 8, bdesc + uint64_t(k * 2),
                             idesc_s, k != 0);
             };
             auto issue_pv = [&](int q, int stage, bool accumulate, int t) {
-                // V tile [64 keys][64 d]: 16 keys per MMA = two 8-row groups = 2048 bytes
+                // V tile [BK keys][64 d]: 16 keys per MMA = two 8-row groups = 2048 bytes
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + stage * ATT_TILE_BYTES), 1024, 1024);
 #pragma unroll
                 for (int k = 0; k < ATT_BK / 16; ++k)
-                    umma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_S + q * 128 + (t & 1) * 64 + k * 8, bdesc + uint64_t(k * 128), idesc_o,
+                    umma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_S + (q * 2 + (t & 1)) * BK + k * 8, bdesc + uint64_t(k * 128), idesc_o,
                             (accumulate || k != 0) ? 1u : 0u);
             };
             auto release_kv = [&](int stage) {
@@ -277,7 +282,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
         const int q = (warp - W_SOFT0) >> 2;    // query tile of this warpgroup
         const int lq = warp & 3;                // TMEM lane quarter
         const uint32_t lane_off = uint32_t(lq * 32) << 16;
-        const uint32_t tSb = tmem_base + lane_off + TM_S + q * 128;
+        const uint32_t tSb = tmem_base + lane_off + TM_S + q * 2 * BK;
         const uint32_t tO = tmem_base + lane_off + TM_O + q * 64;
         const int row = q_row0 + q * ATT_BQ + lq * 32 + lane;
 
@@ -316,21 +321,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
             const int buf = t & 1;
             mbar_wait(&s_full[q * 2 + buf], (t >> 1) & 1);
             tc_fence_after();
-            uint32_t s[64];
+            uint32_t s[BK];
             {
                 uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
                 uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-                tmem_ld32(tSb + buf * 64, s0);
-                tmem_ld32(tSb + buf * 64 + 32, s1);
+                tmem_ld32(tSb + buf * BK, s0);
+                tmem_ld32(tSb + buf * BK + 32, s1);
+                if constexpr (BK == 80) {
+                    uint32_t(&s2)[16] = *reinterpret_cast<uint32_t(*)[16]>(&s[64]);
+                    tmem_ld16(tSb + buf * BK + 64, s2);
+                }
                 tmem_ld_wait();
             }
-            const int valid = S - t * ATT_BK;  // keys valid in this tile (>= 64 except for the last tile)
+            const int valid = S - t * ATT_BK;  // keys valid in this tile (>= BK except for the last tile)
             if (valid < ATT_BK) {
 #pragma unroll
-                for (int i = 0; i < 64; ++i)
+                for (int i = 0; i < BK; ++i)
                     if (i >= valid) s[i] = __float_as_uint(-INFINITY);
             }
-            uint32_t pk[32];
+            uint32_t pk[BK / 2];
             float tsum;
             bool redo = (t == 0);
             if (!redo) {
@@ -339,7 +348,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 uint64_t acc0 = 0ull, acc1 = 0ull;
                 float xmax = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 64; i += 8) {
+                for (int i = 0; i < BK; i += 8) {
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
                         const uint64_t X = ffma2(pack2(__uint_as_float(s[i + 2 * h]), __uint_as_float(s[i + 2 * h + 1])), C2, M2);
@@ -363,7 +372,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 const bool bad = !(tsum < ATT_SUM_LIMIT) || (xmax > ATT_P_LIMIT_LOG2);
                 redo = __any_sync(0xffffffffu, bad);
             }
-            // P(t) is stored over the first 32 columns of its own score buffer S[q][t&1] (dead once it is in registers).  That
+            // P(t) is stored over the first BK/2 columns of its own score buffer S[q][t&1] (dead once it is in registers).  That
             // buffer's previous tenant P(t-2) was consumed before S(t) could be written (the tensor pipe executes in order),
             // so the store needs no barrier wait; only the rare O rescale must know that PV_q(t-1) has finished.
             if (t != 0 && redo) {
@@ -374,7 +383,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 // ---- exact-max path (tile 0, or a probability would leave the 2^64 window): move the reference
                 float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 64; i += 4) {
+                for (int i = 0; i < BK; i += 4) {
                     mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
                     mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
                 }
@@ -397,7 +406,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 mneg = -m_new * scale_log2;
                 float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 64; i += 2) {
+                for (int i = 0; i < BK; i += 2) {
                     const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, mneg));
                     const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg));
                     a0 += p0;
@@ -407,7 +416,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 tsum = a0 + a1;
             }
             l_sum += tsum;
-            tmem_st32(tSb + buf * 64, pk);
+            {
+                const uint32_t(&p0)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]);
+                tmem_st32(tSb + buf * BK, p0);
+                if constexpr (BK == 80) {
+                    const uint32_t(&p1)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&pk[32]);
+                    tmem_st8(tSb + buf * BK + 32, p1);
+                }
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -451,8 +467,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
     if (dbg && threadIdx.x == 0) {   // profiling aid: per-CTA SM cycles and wall nanoseconds -> effective SM clock of this launch
         unsigned long long t1;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        atomicAdd(dbg, (unsigned long long)(clock64() - dbg_c0));
+        const unsigned long long cyc = (unsigned long long)(clock64() - dbg_c0);
+        atomicAdd(dbg, cyc);
         atomicAdd(dbg + 1, t1 - dbg_t0);
+        // per-CTA record (start ns, end ns, cycles): the SM clock as a function of time THROUGH the launch (tools/instep_ab.py)
+        unsigned long long* rec = dbg + 2 + 3ull * (blockIdx.x + gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z));
+        rec[0] = dbg_t0;
+        rec[1] = t1;
+        rec[2] = cyc;
     }
 }
 
@@ -462,18 +484,23 @@ using namespace s2v;
 
 namespace {
 
-// Shipped configuration (profiles/r02_summary.md): 1 polynomial pair in 8, 200 ns start skew of the second warpgroup.
+// Shipped configuration (profiles/r02_summary.md, interleaved A/B isolated, in-step and by energy per launch): 64-key tiles,
+// 1 polynomial pair in 8, 200 ns start skew of the second warpgroup, issuing warps numbered above the softmax warps (HI) and K/V
+// multicast across a 2-CTA cluster (MC): -1.9 % joules per launch against the round-1 numbering without multicast.
 constexpr int ATT_SKEW_NS_DEFAULT = 200;
 #ifndef S2V_ATTN_HI
-#define S2V_ATTN_HI 0
+#define S2V_ATTN_HI 1
 #endif
 #ifndef S2V_ATTN_MC
-#define S2V_ATTN_MC 0
+#define S2V_ATTN_MC 1
+#endif
+#ifndef S2V_ATTN_BK
+#define S2V_ATTN_BK 64
 #endif
 
 using attn_kern_t = void (*)(const CUtensorMap, const bf16*, bf16*, int, int, float, int, unsigned long long*);
 
-int launch_attn(attn_kern_t kern, bool mc, const void* qkv, void* o, int B, int S, int H, float softmax_scale, int skew_ns,
+int launch_attn(attn_kern_t kern, int bk, bool mc, const void* qkv, void* o, int B, int S, int H, float softmax_scale, int skew_ns,
                 unsigned long long* dbg, cudaStream_t stream, const char* who) {
     if (!qkv || !o) return set_error(S2V_E_BADARG, "s2v_attn_fwd: null pointer");
     if (B <= 0 || S <= 0 || H <= 0) return set_error(S2V_E_BADARG, "s2v_attn_fwd: empty problem");
@@ -484,16 +511,16 @@ int launch_attn(attn_kern_t kern, bool mc, const void* qkv, void* o, int B, int 
     const uint64_t row_bytes = (uint64_t)3 * H * ATT_D * 2;
     const uint64_t dims[4] = {(uint64_t)ATT_D, (uint64_t)3 * H, (uint64_t)S, (uint64_t)B};
     const uint64_t strides[4] = {2, (uint64_t)ATT_D * 2, row_bytes, row_bytes * (uint64_t)S};
-    const uint32_t box[4] = {ATT_D, 1, uint32_t(mc ? ATT_BK / 2 : ATT_BK), 1};
+    const uint32_t box[4] = {ATT_D, 1, uint32_t(mc ? bk / 2 : bk), 1};
     if ((rc = make_tmap_nd_bf16(&tm, qkv, 4, dims, strides, box))) return rc;
-    if ((rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), ATT_SMEM_BYTES, "cudaFuncSetAttribute(attn)"))) return rc;
+    if ((rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), att_smem_bytes(bk), "cudaFuncSetAttribute(attn)"))) return rc;
     int qblocks = (S + ATT_BQ * ATT_QTILES - 1) / (ATT_BQ * ATT_QTILES);
     if (mc) qblocks = (qblocks + 1) & ~1;
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(qblocks, H, B);
     cfg.blockDim = dim3(ATT_THREADS);
-    cfg.dynamicSmemBytes = ATT_SMEM_BYTES;
+    cfg.dynamicSmemBytes = att_smem_bytes(bk);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -510,24 +537,25 @@ int launch_attn(attn_kern_t kern, bool mc, const void* qkv, void* o, int B, int 
 }  // namespace
 
 extern "C" int s2v_attn_fwd(const void* qkv, void* o, int32_t B, int32_t S, int32_t H, float softmax_scale, void* stream_) {
-    return launch_attn(attn_fwd_kernel<ATT_POLY16_DEFAULT, S2V_ATTN_HI != 0, S2V_ATTN_MC != 0>, S2V_ATTN_MC != 0, qkv, o, B, S, H,
+    return launch_attn(attn_fwd_kernel<S2V_ATTN_BK, ATT_POLY16_DEFAULT, S2V_ATTN_HI != 0, S2V_ATTN_MC != 0>, S2V_ATTN_BK, S2V_ATTN_MC != 0, qkv, o, B, S, H,
                        softmax_scale, ATT_SKEW_NS_DEFAULT, nullptr, static_cast<cudaStream_t>(stream_), "attn_fwd_kernel");
 }
 
 #ifdef S2V_ATTN_EXPERIMENT
 // Measurement-only entry point (tools/build_attn_exp.py -> tools/bin/libattn_exp.so; NOT part of libs2v_b200.so): every
 // (polynomial fraction, warp numbering, multicast) combination of the same kernel for in-process interleaved A/B runs, plus the
-// per-CTA cycle / nanosecond counters.  variant: bit 0 = HI, bit 1 = MC.
+// per-CTA cycle / nanosecond counters.  variant: bit 0 = HI, bit 1 = MC, bit 2 = 80-key tiles.
 extern "C" __attribute__((visibility("default"))) int s2v_attn_fwd_exp(const void* qkv, void* o, int32_t B, int32_t S, int32_t H,
                                                                        float softmax_scale, int32_t variant, int32_t poly16,
                                                                        int32_t skew_ns, void* dbg_u64x2, void* stream_) {
-    static const attn_kern_t kerns[3][4] = {
-        {attn_fwd_kernel<0, false, false>, attn_fwd_kernel<0, true, false>, attn_fwd_kernel<0, false, true>, attn_fwd_kernel<0, true, true>},
-        {attn_fwd_kernel<1, false, false>, attn_fwd_kernel<1, true, false>, attn_fwd_kernel<1, false, true>, attn_fwd_kernel<1, true, true>},
-        {attn_fwd_kernel<2, false, false>, attn_fwd_kernel<2, true, false>, attn_fwd_kernel<2, false, true>, attn_fwd_kernel<2, true, true>}};
-    if (poly16 < 0 || poly16 > 2 || variant < 0 || variant > 3 || skew_ns < 0 || skew_ns > 100000)
-        return set_error(S2V_E_BADARG, "s2v_attn_fwd_exp: poly16 0..2, variant 0..3, skew_ns 0..100000");
-    return launch_attn(kerns[poly16][variant], (variant & 2) != 0, qkv, o, B, S, H, softmax_scale, skew_ns,
+#define S2V_ROW(P) {attn_fwd_kernel<64, P, false, false>, attn_fwd_kernel<64, P, true, false>, attn_fwd_kernel<64, P, false, true>, \
+                    attn_fwd_kernel<64, P, true, true>, attn_fwd_kernel<80, P, false, false>, attn_fwd_kernel<80, P, true, false>, \
+                    attn_fwd_kernel<80, P, false, true>, attn_fwd_kernel<80, P, true, true>}
+    static const attn_kern_t kerns[3][8] = {S2V_ROW(0), S2V_ROW(1), S2V_ROW(2)};
+#undef S2V_ROW
+    if (poly16 < 0 || poly16 > 2 || variant < 0 || variant > 7 || skew_ns < 0 || skew_ns > 100000)
+        return set_error(S2V_E_BADARG, "s2v_attn_fwd_exp: poly16 0..2, variant 0..7, skew_ns 0..100000");
+    return launch_attn(kerns[poly16][variant], (variant & 4) ? 80 : 64, (variant & 2) != 0, qkv, o, B, S, H, softmax_scale, skew_ns,
                        static_cast<unsigned long long*>(dbg_u64x2), static_cast<cudaStream_t>(stream_), "attn_fwd_kernel(exp)");
 }
 #endif

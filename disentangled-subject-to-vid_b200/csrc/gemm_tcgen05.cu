@@ -24,7 +24,6 @@ constexpr int GEMM_THREADS = 192;
 struct GemmKParams {
     int M, N, K, K2;
     int group_m;        // row-blocks per rasterisation group (see tile_coords)
-    unsigned long long pol_a, pol_b;   // L2 eviction priority of the activation / weight TMA loads (see pick_l2_policy)
     int lora_group_n;
     const bf16* bias;
     bf16* out;
@@ -103,11 +102,12 @@ __device__ __forceinline__ void head_norm_rope(float (&f)[64], const bf16* __res
     }
 }
 
-template <int BN>
+template <int BN, bool TWO = false>
 struct GemmCfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    // TWO (cta_group::2): a CTA pair owns a 256 x BN tile; each CTA stages its own 128 A rows and HALF of the B rows
+    static constexpr int STAGES = TWO ? 6 : (BN == 256) ? 4 : 6;
     static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
-    static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+    static constexpr uint32_t B_BYTES = (TWO ? BN / 2 : BN) * GEMM_BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -126,12 +126,13 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
     n_blk = r / gm;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool TWO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                     const GemmKParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, TWO>;
+    static_assert(!TWO || (EPI != S2V_EPI_CONV_T), "the swapped-operand convolution runs one CTA per tile");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -145,7 +146,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int lane = threadIdx.x & 31;
 
     constexpr bool TR = (EPI == S2V_EPI_CONV_T);
-    constexpr int TILE_M = TR ? BN : GEMM_BM;          // problem rows (TR: output positions) per tile
+    constexpr int TILE_M = TR ? BN : TWO ? 2 * GEMM_BM : GEMM_BM;   // problem rows per tile (TR: output positions; TWO: the pair's 256)
+    // TWO: both CTAs of a pair walk the same tile sequence; this CTA owns rows [m_blk * 256 + rank * 128, +128) of every tile
+    const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
+    const int first_tile = TWO ? int(blockIdx.x >> 1) : int(blockIdx.x);
+    const int tile_step = TWO ? int(gridDim.x >> 1) : int(gridDim.x);
     const int num_m = (p.M + TILE_M - 1) / TILE_M;
     const int num_n = TR ? 1 : (p.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
@@ -166,11 +171,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], TWO ? 8 : 4);  // one arrive per epilogue warp (of both CTAs: the leader's MMA thread waits)
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (TWO) {
+        __syncwarp();
+        cluster_sync_all();     // the pair's barriers exist before either CTA signals them
+    }
+    if (warp == 1) {
+        if (TWO) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -181,15 +192,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 int m_blk, n_blk;
                 tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
-                const int m0 = m_blk * TILE_M, n0 = n_blk * BN;
+                const int m0 = m_blk * TILE_M + int(cta_rank) * GEMM_BM, n0 = n_blk * BN;
+                const int nb0 = n0 + int(cta_rank) * (BN / 2);    // TWO: this CTA's half of the tile's B rows
                 const int lora_col0 = kb2 ? (n0 / p.lora_group_n) * p.K2 : 0;
                 for (int kb = 0; kb < kb_total; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
+                    if (TWO) {
+                        // the leader's barrier counts the bytes of BOTH CTAs' loads (tma_load_2d_pair signals it from the peer too)
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        if (kb < kb1) {
+                            if (EPI == S2V_EPI_CONV) {
+                                const int tap = kb / p.cin_blocks;
+                                tma_load_2d_pair(&tmA, &full_bar[stage], sa, (kb - tap * p.cin_blocks) * GEMM_BK, p.a_row0 + m0 + p.tap_off[tap]);
+                            } else {
+                                tma_load_2d_pair(&tmA, &full_bar[stage], sa, kb * GEMM_BK, m0);
+                            }
+                            tma_load_2d_pair(&tmB, &full_bar[stage], sb, kb * GEMM_BK, nb0);
+                        } else {
+                            const int kk = (kb - kb1) * GEMM_BK;
+                            tma_load_2d_pair(&tmA2, &full_bar[stage], sa, lora_col0 + kk, m0);
+                            tma_load_2d_pair(&tmB2, &full_bar[stage], sb, kk, nb0);
+                        }
+                        if (++stage == Cfg::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     if (TR) {   // weights -> M-side slot (128 rows), 256 tap-shifted activation rows -> N-side slot
                         const int tap = kb / p.cin_blocks;
@@ -201,13 +235,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             tma_load_2d(&tmA, &full_bar[stage], sa, (kb - tap * p.cin_blocks) * GEMM_BK,
                                         p.a_row0 + m0 + p.tap_off[tap]);
                         } else {
-                            tma_load_2d_hint(&tmA, &full_bar[stage], sa, kb * GEMM_BK, m0, p.pol_a);
+                            tma_load_2d(&tmA, &full_bar[stage], sa, kb * GEMM_BK, m0);
                         }
-                        tma_load_2d_hint(&tmB, &full_bar[stage], sb, kb * GEMM_BK, n0, p.pol_b);
+                        tma_load_2d(&tmB, &full_bar[stage], sb, kb * GEMM_BK, n0);
                     } else {
                         const int kk = (kb - kb1) * GEMM_BK;
-                        tma_load_2d_hint(&tmA2, &full_bar[stage], sa, lora_col0 + kk, m0, p.pol_a);
-                        tma_load_2d_hint(&tmB2, &full_bar[stage], sb, kk, n0, p.pol_b);
+                        tma_load_2d(&tmA2, &full_bar[stage], sa, lora_col0 + kk, m0);
+                        tma_load_2d(&tmB2, &full_bar[stage], sb, kk, n0);
                     }
                     if (++stage == Cfg::STAGES) {
                         stage = 0;
@@ -220,12 +254,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ------------------------------------------------------------------ MMA issuer
         // single elected thread for the whole loop (see attn_tcgen05.cu: `if (lane == 0)` around each tcgen05.mma makes the
         // compiler wrap it in a warp-uniformisation loop)
-        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
-        if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * GEMM_BM : GEMM_BM, BN, 0, 0);
+        if (cta_rank == 0 && elect_one()) {      // TWO: the leader CTA's thread issues for the pair
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -240,10 +274,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
                         // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) field
-                        umma_ss(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+                        if (TWO) umma_ss_pair(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
+                        else umma_ss(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);
+                    if (TWO) {   // both CTAs' producers (stage free) and both CTAs' epilogue warps (accumulator ready) are told
+                        umma_commit_pair(&empty_bar[stage], 3);
+                        if (kb == kb_total - 1) umma_commit_pair(&tmem_full[acc], 3);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);
+                    }
                     if (++stage == Cfg::STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -256,9 +296,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int q = warp & 3;  // TMEM lane quarter this warp may touch
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             int m_blk, n_blk;
             tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
+            if (TWO) m_blk = m_blk * 2 + int(cta_rank);     // this CTA's 128-row block of the pair's tile
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -550,15 +591,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (TWO) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+            }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (TWO) cluster_sync_all();    // neither CTA frees its TMEM or retires while the pair's MMAs / barrier arrivals can still touch it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (TWO) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -571,48 +615,52 @@ struct ConvExtra {
     long long ldres;
 };
 
-// Rasterisation group height: the group's activation panel (group_m x 128 rows x K bf16) should stay L2-resident while the
-// weights stream past it (126 MB L2; measurements in profiles/r02_summary.md).  S2V_GEMM_GROUP_M overrides for measurements.
-static int pick_group_m(int M, int K) {
+// Rasterisation group height (in 128-row blocks).  DRAM reads of a launch ~ |X| + |W| * num_m / group_m as long as the group's
+// activation panel (group_m x 128 rows x K bf16) survives in L2 while the weights stream past it; measured on B200 with ncu
+// (profiles/r02_summary.md, "GEMM rasterisation"): K = 3072 + LoRA: 16 -> 1.72 GB, 32 -> 1.04, 40 -> 0.89, 48 -> 1.01, 64 -> 1.74 (panel
+// no longer fits), 96 -> 5.4 GB for the FFN-up projection (0.34 GB of operands) — the optimum is a ~31 MB panel.  When the whole
+// weight matrix is small enough to stay resident anyway (out-projection: 19 MB) short groups are better (12: 0.51 GB, 48: 0.72 GB).
+// S2V_GEMM_GROUP_M overrides for measurements.
+static int pick_group_m(int M, int N, int K) {
     static const int forced = [] { const char* e = getenv("S2V_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
     if (forced > 0) return forced;
-    (void)M; (void)K;
-    return GEMM_GROUP_M_DEFAULT;
+    (void)M;
+    if ((long long)N * K * 2 <= (32ll << 20)) return 12;
+    const long long panel_row = 128ll * K * 2;
+    long long g = ((31ll << 20) + panel_row / 2) / panel_row;
+    return int(g < 8 ? 8 : g > 64 ? 64 : g);
 }
 
-// L2 eviction priority of the two operand streams.  Every rasterisation group re-reads the WHOLE weight matrix (19 - 57 - 76 MB
-// for the out / QKV / FFN projections of the 5B model) while the activations stream through once per group: with the default
-// policy the 0.5 - 1.4 GB of activations and outputs of a launch push the weights out of the 126 MB L2 between groups (measured:
-// FFN-down reads 3.8 GB from DRAM for 1.25 GB of operands, profiles/r02_summary.md).  Mode 1 marks the weight loads evict-last,
-// mode 2 additionally marks the activation loads evict-first.  S2V_GEMM_L2_HINT overrides for measurements.
-static void pick_l2_policy(unsigned long long* pol_a, unsigned long long* pol_b) {
-    static const int mode = [] { const char* e = getenv("S2V_GEMM_L2_HINT"); return e ? atoi(e) : 0; }();
-    *pol_a = mode == 2 ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
-    *pol_b = mode >= 1 ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+// The big projections run as CTA pairs (cta_group::2, 256 x 256 tiles): per MMA each SM stages and reads half of the B rows, so
+// shared-memory operand traffic and L2 -> SM traffic per flop drop by a third against the 128 x 256 single-CTA tile — under the
+// 1 kW cap that is what the sustained GEMM rate responds to (profiles/r02_summary.md).  S2V_GEMM_2CTA=0 keeps single CTAs (A/B).
+static bool use_cta_pairs(int M, int N) {
+    static const int forced = [] { const char* e = getenv("S2V_GEMM_2CTA"); return e ? atoi(e) : -1; }();
+    if (forced >= 0) return forced != 0;
+    return M >= 2048 && N >= 256;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool TWO = false>
 static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const ConvExtra* conv = nullptr, const s2v_qk_norm_args* qk = nullptr) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, TWO>;
     CUtensorMap tmA, tmB, tmA2, tmB2;
     int rc;
     constexpr bool TR = (EPI == S2V_EPI_CONV_T);   // operands swapped: BN activation rows per box, 128 weight rows
+    constexpr int B_BOX = TR ? GEMM_BM : TWO ? BN / 2 : BN;
     if ((rc = make_tmap_2d_bf16(&tmA, a->x, conv ? conv->cin : a->K, conv ? conv->a_rows : a->M, a->ldx, GEMM_BK, TR ? BN : GEMM_BM))) return rc;
-    if ((rc = make_tmap_2d_bf16(&tmB, a->w, a->K, a->N, a->ldw, GEMM_BK, TR ? GEMM_BM : BN))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tmB, a->w, a->K, a->N, a->ldw, GEMM_BK, B_BOX))) return rc;
     const int K2 = a->lora_t ? a->lora_r : 0;
     if (K2) {
         const int groups = (a->N + a->lora_group_n - 1) / a->lora_group_n;
         if ((rc = make_tmap_2d_bf16(&tmA2, a->lora_t, (int64_t)groups * K2, a->M, a->ldt, GEMM_BK, GEMM_BM))) return rc;
-        if ((rc = make_tmap_2d_bf16(&tmB2, a->lora_b, K2, a->N, a->ldb, GEMM_BK, BN))) return rc;
+        if ((rc = make_tmap_2d_bf16(&tmB2, a->lora_b, K2, a->N, a->ldb, GEMM_BK, B_BOX))) return rc;
     } else {
         tmA2 = tmA;
         tmB2 = tmB;
     }
     GemmKParams p;
     p.M = a->M; p.N = a->N; p.K = a->K; p.K2 = K2;
-    p.group_m = pick_group_m(a->M, a->K + K2);
-    pick_l2_policy(&p.pol_a, &p.pol_b);
-    if (conv) p.pol_a = p.pol_b = L2_EVICT_NORMAL;   // the activation volume is the re-read operand there (27 taps)
+    p.group_m = pick_group_m(a->M, a->N, a->K + K2);
     p.lora_group_n = a->lora_group_n > 0 ? a->lora_group_n : a->N;
     p.bias = static_cast<const bf16*>(a->bias);
     p.out = static_cast<bf16*>(a->out);
@@ -636,9 +684,29 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
         for (int i = 0; i < 27; ++i) p.tap_off[i] = i < conv->taps ? conv->tap_off[i] : 0;
     }
 
-    auto kern = gemm_tcgen05_kernel<BN, EPI>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI, TWO>;
     if ((rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, "cudaFuncSetAttribute(gemm)"))) return rc;
-    const int num_tiles = TR ? (a->M + BN - 1) / BN : ((a->M + GEMM_BM - 1) / GEMM_BM) * ((a->N + BN - 1) / BN);
+    constexpr int TILE_M = TWO ? 2 * GEMM_BM : GEMM_BM;
+    const int num_tiles = TR ? (a->M + BN - 1) / BN : ((a->M + TILE_M - 1) / TILE_M) * ((a->N + BN - 1) / BN);
+    if (TWO) {
+        if (p.group_m > 1) p.group_m = (p.group_m + 1) / 2;      // group height is counted in tiles (256-row pair-blocks here)
+        const int clusters = num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, p);
+        if (e != cudaSuccess) return set_cuda_error(e, "gemm_tcgen05_kernel(cta pair)");
+        return check_launch("gemm_tcgen05_kernel(cta pair)");
+    }
     const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
     return check_launch("gemm_tcgen05_kernel");
@@ -666,12 +734,16 @@ extern "C" int s2v_linear(const s2v_linear_args* a, void* stream_) {
     // 256-wide tiles for the big projections, 128-wide when N is small or a LoRA group boundary is not 256-aligned
     const int gn = (a->lora_t && a->lora_group_n > 0) ? a->lora_group_n : a->N;
     const bool wide = (a->N >= 256) && (gn % 256 == 0 || !a->lora_t || gn == a->N);
+    const bool two = wide && use_cta_pairs(a->M, a->N);
     switch (a->epilogue) {
         case S2V_EPI_BIAS:
+            if (two) return launch_gemm<256, S2V_EPI_BIAS, true>(a, stream);
             return wide ? launch_gemm<256, S2V_EPI_BIAS>(a, stream) : launch_gemm<128, S2V_EPI_BIAS>(a, stream);
         case S2V_EPI_BIAS_GELU:
+            if (two) return launch_gemm<256, S2V_EPI_BIAS_GELU, true>(a, stream);
             return wide ? launch_gemm<256, S2V_EPI_BIAS_GELU>(a, stream) : launch_gemm<128, S2V_EPI_BIAS_GELU>(a, stream);
         case S2V_EPI_GATE_RESIDUAL:
+            if (two) return launch_gemm<256, S2V_EPI_GATE_RESIDUAL, true>(a, stream);
             return wide ? launch_gemm<256, S2V_EPI_GATE_RESIDUAL>(a, stream)
                         : launch_gemm<128, S2V_EPI_GATE_RESIDUAL>(a, stream);
         default:
@@ -697,6 +769,7 @@ extern "C" int s2v_qkv_lora_norm_rope(const s2v_linear_args* a, const s2v_qk_nor
     if (rc) return rc;
     const int gn = qk->H * 64;
     const bool wide = (gn % 256 == 0) || !a->lora_t;
+    if (wide && use_cta_pairs(a->M, a->N)) return launch_gemm<256, S2V_EPI_QKV_NORM_ROPE, true>(a, stream, nullptr, qk);
     return wide ? launch_gemm<256, S2V_EPI_QKV_NORM_ROPE>(a, stream, nullptr, qk) : launch_gemm<128, S2V_EPI_QKV_NORM_ROPE>(a, stream, nullptr, qk);
 }
 extern "C" int s2v_outproj_lora_gate_residual(const s2v_linear_args* a, void* stream) {

@@ -156,3 +156,11 @@ extern "C" int s2v_device_check(int dev) {
     if (prop.major != 10) return s2v::set_error(S2V_E_NO_DEVICE, "device is not sm_100 (B200)");
     return 0;
 }
+
+extern "C" int64_t s2v_workspace_bytes(int32_t B, int32_t S, int32_t D, int32_t ff_dim, int32_t lora_cols, int32_t n_mod) {
+    if (B <= 0 || S <= 0 || D <= 0 || ff_dim <= 0 || lora_cols < 0 || n_mod <= 0) return s2v::set_error(S2V_E_BADARG, "s2v_workspace_bytes: bad geometry");
+    auto up = [](int64_t b) { return (b + 255) & ~int64_t(255); };
+    const int64_t rows = int64_t(B) * S;
+    const int64_t lt_cols = lora_cols > 8 ? lora_cols : 8;
+    return 3 * up(rows * D * 2) + up(rows * 3 * D * 2) + up(rows * ff_dim * 2) + up(rows * lt_cols * 2) + up(int64_t(n_mod) * B * 6 * D * 4);
+}

@@ -156,18 +156,37 @@ def pack_block(block, merge_lora: bool = False) -> PackedBlock:
 
 
 class Workspace:
-    """Activation buffers for one (B, S) geometry; allocated once, reused by every block and every step."""
+    """Activation buffers for one (B, S) geometry; ONE caller-side allocation of `s2v_workspace_bytes(...)` bytes carved in the
+    order the header documents, reused by every block and every step (the library itself allocates nothing)."""
 
     def __init__(self, B: int, S: int, D: int, ff_dim: int, max_r3: int, n_mod: int, device):
+        from . import _lib
         self.B, self.S, self.D = B, S, D
-        e = lambda *s, dt=BF16: torch.empty(*s, device=device, dtype=dt)  # noqa: E731
-        self.h = e(B, S, D)
-        self.xn = e(B, S, D)
-        self.att = e(B, S, D)
-        self.qkv = e(B, S, 3 * D)
-        self.ffh = e(B, S, ff_dim)
-        self.lt = e(B * S, max(max_r3, 8))
-        self.mod = e(n_mod, B, 6 * D, dt=torch.float32)
+        total = _lib.load().s2v_workspace_bytes(B, S, D, ff_dim, max_r3, n_mod)
+        if total < 0:
+            raise RuntimeError(f"s2v_workspace_bytes rejected the geometry B={B} S={S} D={D} ff={ff_dim}")
+        self.nbytes = int(total)
+        self.arena = torch.empty(self.nbytes, device=device, dtype=torch.uint8)
+        off = 0
+
+        def carve(shape, dt=BF16):
+            nonlocal off
+            n = 1
+            for d in shape:
+                n *= d
+            nb = n * (2 if dt == BF16 else 4)
+            t = self.arena[off:off + nb].view(dt).view(*shape)
+            off += (nb + 255) & ~255
+            return t
+
+        self.h = carve((B, S, D))
+        self.xn = carve((B, S, D))
+        self.att = carve((B, S, D))
+        self.qkv = carve((B, S, 3 * D))
+        self.ffh = carve((B, S, ff_dim))
+        self.lt = carve((B * S, max(max_r3, 8)))
+        self.mod = carve((n_mod, B, 6 * D), torch.float32)
+        assert off == self.nbytes, (off, self.nbytes)
 
 
 class BlockRunner:

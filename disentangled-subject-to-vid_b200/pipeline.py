@@ -48,6 +48,9 @@ class CustomCogVideoXPipeline:
         self._guidance_scale = 1.0
         self._num_timesteps = 0
         self.interrupt = False
+        self._rope_cache: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._cfg_plan = None      # parallel.ShardPlan(mode="cfg") when this rank runs one CFG half (enable_cfg_parallel)
+        self._cfg_xchg = None
 
     # ------------------------------------------------------------------ helpers (base pipeline surface)
     @property
@@ -153,9 +156,30 @@ class CustomCogVideoXPipeline:
         """Joint [ref | video] cos/sin table (pipeline_cogvideox.py:436-460 + custom_cogvideox_pipe.py:223-235)."""
         cfg = self.transformer.config
         g = lambda k, d: cfg[k] if isinstance(cfg, dict) else getattr(cfg, k, d)  # noqa: E731
-        cos, sin = tables.joint_rope_table(height, width, latent_frames, g("attention_head_dim", 64), g("patch_size", 2),
-                                           self.vae_scale_factor_spatial)
-        return cos.to(device), sin.to(device)
+        key = (height, width, latent_frames, g("attention_head_dim", 64), g("patch_size", 2), self.vae_scale_factor_spatial, str(device))
+        if key not in self._rope_cache:   # the reference rebuilds the table on the host every call; it only depends on the geometry
+            cos, sin = tables.joint_rope_table(*key[:6])
+            if len(self._rope_cache) >= 4:
+                self._rope_cache.clear()
+            self._rope_cache[key] = (cos.to(device), sin.to(device))
+        return self._rope_cache[key]
+
+    # ------------------------------------------------------------------ CFG halves on two GPUs (parallel.py)
+    def enable_cfg_parallel(self, shard_plan, record_times: bool = False):
+        """This rank runs ONE classifier-free-guidance half (shard_plan.cfg_half: 0 = negative prompt, 1 = prompt) of the prompts
+        it is called with; its pair rank runs the other half.  Per step the pair exchanges the model output (one NCCL
+        all_gather_into_tensor on a side stream, parallel.PairExchange) and both apply the identical bit-exact CFG + scheduler
+        kernel, so `__call__` returns the same latents on both ranks — bit-identical to the single-GPU call of the same build.
+        Collective: every rank of the job must call this (it creates the pair process groups)."""
+        from .parallel import PairExchange
+        if shard_plan.mode != "cfg":
+            raise ValueError("enable_cfg_parallel needs a ShardPlan in 'cfg' mode (parallel.plan(..., mode='cfg'))")
+        self._cfg_plan = shard_plan
+        self._cfg_xchg = PairExchange(shard_plan, record_times=record_times)
+        return self
+
+    def disable_cfg_parallel(self):
+        self._cfg_plan = self._cfg_xchg = None
 
     def decode_latents(self, latents: torch.Tensor) -> torch.Tensor:
         if self.vae is None:
@@ -202,7 +226,10 @@ class CustomCogVideoXPipeline:
             prompt, negative_prompt=negative_prompt, do_classifier_free_guidance=do_cfg, num_videos_per_prompt=num_videos_per_prompt,
             prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds, max_sequence_length=max_sequence_length,
             device=device)
-        prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0).to(device=device, dtype=BF16)
+        if self._cfg_plan is None:
+            prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0).to(device=device, dtype=BF16)
+        else:   # CFG halves on two GPUs: this rank's half of the [negative | positive] batch of S/custom_cogvideox_pipe.py:196
+            prompt_embeds = (negative_prompt_embeds if self._cfg_plan.cfg_half == 0 else prompt_embeds).to(device=device, dtype=BF16)
 
         if timesteps is None:
             self.scheduler.set_timesteps(num_inference_steps, device=device)
@@ -240,12 +267,21 @@ class CustomCogVideoXPipeline:
         for i, t in enumerate(steps_host):
             if self.interrupt:
                 break
-            model_in[:P].copy_(latents)     # torch.cat([latents] * 2); scale_model_input is the identity
-            model_in[P:].copy_(latents)
-            noise_pred = self.transformer(hidden_states=model_in, encoder_hidden_states=prompt_embeds, ref_img_states=ref,
-                                          timestep=t_dev[i:i + 1].expand(2 * P), image_rotary_emb=image_rotary_emb,
-                                          ref_image_rotary_emb=ref_image_rotary_emb, attention_kwargs=attention_kwargs,
-                                          return_dict=False, eval=True)[0]
+            if self._cfg_plan is None:
+                model_in[:P].copy_(latents)     # torch.cat([latents] * 2); scale_model_input is the identity
+                model_in[P:].copy_(latents)
+                noise_pred = self.transformer(hidden_states=model_in, encoder_hidden_states=prompt_embeds, ref_img_states=ref,
+                                              timestep=t_dev[i:i + 1].expand(2 * P), image_rotary_emb=image_rotary_emb,
+                                              ref_image_rotary_emb=ref_image_rotary_emb, attention_kwargs=attention_kwargs,
+                                              return_dict=False, eval=True)[0]
+            else:
+                # one CFG half here, the other on the pair rank (eval=False: the reference tokens are not doubled along batch
+                # because the batch is not); then (uncond, cond) are exchanged inside the pair
+                half = self.transformer(hidden_states=latents, encoder_hidden_states=prompt_embeds, ref_img_states=ref,
+                                        timestep=t_dev[i:i + 1].expand(P), image_rotary_emb=image_rotary_emb,
+                                        ref_image_rotary_emb=ref_image_rotary_emb, attention_kwargs=attention_kwargs,
+                                        return_dict=False, eval=False)[0]
+                noise_pred = self._cfg_xchg.both_halves(half)
             self._guidance_scale = self._guidance_for_step(guidance_scale, use_dynamic_cfg, i, num_inference_steps)
             # .float() -> u + g (t - u) -> scheduler step -> .to(bf16), fused and bit-exact
             if isinstance(self.scheduler, CogVideoXDPMScheduler):   # S/custom_cogvideox_pipe.py:288-295

@@ -181,6 +181,12 @@ def _call(name, *args):
     _lib.check(getattr(lib, name)(*args), name)
 
 
+# Measurement hook (bench.py): when set to a dict, every convolution launch adds its FLOPs — "algorithmic" = 2 x output positions
+# x Cout x taps x Cin over the T x H x W real positions (what a FLOP counter reports for the reference's conv3d / conv2d calls),
+# "launched" = the same over the padded T x (H+2) x (W+2) rows the implicit GEMM actually computes (the border ring is waste).
+CONV_FLOPS: Optional[Dict[str, float]] = None
+
+
 def out_frames(T: int, compress_time: bool) -> int:
     """Frames after one CogVideoXUpsample3D (upsampling.py:385-405)."""
     if not compress_time or T == 1:
@@ -316,6 +322,11 @@ class VaeDecoderEngine:
         a.res, a.ldres = (res.data_ptr(), res.shape[-1]) if res is not None else (None, 0)
         a.out, a.ldo = out.data_ptr(), out.shape[-1]
         a.T, a.t_pad, a.Hp, a.Wp, a.cin, a.cout, a.taps = T, 2, H + 2, W + 2, cv.cin, cv.cout, cv.taps
+        if CONV_FLOPS is not None:
+            per_pos = 2.0 * cv.cout * cv.taps * cv.cin
+            CONV_FLOPS["algorithmic"] = CONV_FLOPS.get("algorithmic", 0.0) + per_pos * T * H * W
+            CONV_FLOPS["launched"] = CONV_FLOPS.get("launched", 0.0) + per_pos * T * (H + 2) * (W + 2)
+            CONV_FLOPS["launches"] = CONV_FLOPS.get("launches", 0) + 1
         _call("s2v_conv_gemm", C.byref(a), _stream())
 
     def _spatialnorm_silu(self, nm: _Norm, x: torch.Tensor, out: torch.Tensor, yb_all: torch.Tensor, T: int, H: int, W: int, Tl: int,

@@ -52,6 +52,11 @@ S2V_API int s2v_abi_version(void);
 S2V_API const char* s2v_last_error(void);
 /* 0 if device `dev` is sm_100 (B200); S2V_E_NO_DEVICE otherwise. */
 S2V_API int s2v_device_check(int dev);
+/* Bytes of caller-owned activation workspace one transformer forward needs (the library allocates nothing):
+ * h, xn, att [B,S,D] + qkv [B,S,3D] + ffh [B,S,ff_dim] in bf16, the LoRA down-projection scratch [B*S, max(lora_cols, 8)] bf16 and
+ * the modulation table [n_mod, B, 6D] fp32, each rounded up to 256 bytes.  Host-only arithmetic (no device needed); negative
+ * on bad arguments.  The buffers may be laid out in one allocation in that order. */
+S2V_API int64_t s2v_workspace_bytes(int32_t B, int32_t S, int32_t D, int32_t ff_dim, int32_t lora_cols, int32_t n_mod);
 
 /* ------------------------------------------------------------------------------------------------ linear + LoRA
  * y[M,N] = x[M,K] * w[N,K]^T (+ bias) (+ lora_t[M, g*r : (g+1)*r] * lora_b[N, r]^T), tcgen05 + TMA, fp32 accumulate,

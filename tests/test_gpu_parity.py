@@ -429,27 +429,37 @@ def _attn_exp():
     return lib
 
 
-def test_attention_kernel_variants_match_shipped(dev):
-    """Every template combination of the attention kernel (warp numbering HI, K/V multicast across a 2-CTA cluster MC) computes the
-    same bits as the shipped entry point: the schedule changes, the arithmetic does not.  Sizes cover an odd number of 256-row
-    query blocks (MC pads the grid with a partner-only CTA), ragged tails and rows whose maximum jumps by > 2^64."""
+def test_attention_kernel_variants_match_shipped(dev, parity):
+    """Every template combination of the attention kernel (bit 0: warp numbering HI, bit 1: K/V multicast across a 2-CTA cluster,
+    bit 2: 80-key instead of 64-key tiles).  Variants that share a tile size compute the SAME bits — the schedule changes, the
+    arithmetic does not; the two tile sizes differ in summation order only and are each compared with torch SDPA in fp32.  The
+    shipped entry point is one of them, bit for bit.  Sizes cover an odd number of 256-row query blocks (MC pads the grid with a
+    partner-only CTA), ragged tails against both tile sizes and rows whose maximum jumps by > 2^64."""
     from s2v_b200 import ops
     exp = _attn_exp()
     torch.manual_seed(3)
-    for (B, S, H, boost) in [(1, 1, 1, None), (1, 65, 2, None), (2, 700, 2, 300), (1, 1500, 1, 64), (1, 3000, 3, 2900)]:
+    for (B, S, H, boost) in [(1, 1, 1, None), (1, 65, 2, None), (1, 81, 1, None), (2, 700, 2, 300), (1, 1500, 1, 64), (1, 3000, 3, 2900)]:
         qkv = torch.randn(B, S, 3 * H * 64, device=dev)
         if boost is not None:
             qkv[:, boost:boost + 3, H * 64:2 * H * 64] *= 40.0
         qkv = qkv.to(BF16)
-        base = torch.empty(B, S, H * 64, device=dev, dtype=BF16)
-        ops.attention(qkv, base, H)
-        for variant in (0, 1, 2, 3):
+        shipped = torch.empty(B, S, H * 64, device=dev, dtype=BF16)
+        ops.attention(qkv, shipped, H)
+        q, k, v = [t.view(B, S, H, 64).transpose(1, 2).float() for t in qkv.chunk(3, dim=-1)]
+        ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
+        outs = {}
+        for variant in range(8):
             out = torch.full((B, S, H * 64), float("nan"), device=dev, dtype=BF16)
             rc = exp.s2v_attn_fwd_exp(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, variant, 1, 200, None,
                                       torch.cuda.current_stream().cuda_stream)
             assert rc == 0, (variant, rc)
             torch.cuda.synchronize()
-            assert torch.equal(out, base), (B, S, H, boost, variant)
+            outs[variant] = out
+            assert torch.equal(out, outs[variant & 4]), (B, S, H, boost, variant)
+        assert torch.equal(shipped, outs[0]) or torch.equal(shipped, outs[4])
+        for base in (0, 4):
+            parity.check(f"attention_variants[bk={80 if base else 64},B={B},S={S},H={H},boost={boost}]", rel_err(outs[base], ref)[0],
+                         default=2e-2, note="torch SDPA fp32 on the same bf16 q,k,v")
 
 
 # ---------------------------------------------------------------------------------------------- DPM scheduler (§8f next row)
@@ -605,12 +615,16 @@ def test_attention_survives_a_warpgroup_that_lags_many_tiles(dev):
     qkv = torch.randn(B, S, 3 * H * 64, generator=g).to(BF16).to(dev)
     base = torch.empty(B, S, H * 64, device=dev, dtype=BF16)
     ops.attention(qkv, base, H)
-    for variant in (0, 1, 2, 3):   # the same source as the shipped kernel, with the start skew as a parameter
-        lagged = torch.empty_like(base)
-        assert exp.s2v_attn_fwd_exp(qkv.data_ptr(), lagged.data_ptr(), B, S, H, 0.125, variant, 1, 100000, None,
-                                    torch.cuda.current_stream().cuda_stream) == 0
-        torch.cuda.synchronize()
-        assert torch.equal(base, lagged), variant
+    outs = {}
+    for variant in range(8):   # the same source as the shipped kernel, with the start skew as a parameter
+        for skew in (200, 100000):
+            out = torch.empty_like(base)
+            assert exp.s2v_attn_fwd_exp(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, variant, 1, skew, None,
+                                        torch.cuda.current_stream().cuda_stream) == 0
+            torch.cuda.synchronize()
+            outs[(variant, skew)] = out
+        assert torch.equal(outs[(variant, 200)], outs[(variant, 100000)]), variant
+    assert torch.equal(base, outs[(0, 200)]) or torch.equal(base, outs[(4, 200)])
 
 
 @pytest.mark.gpu
@@ -634,3 +648,105 @@ def test_attention_edge_sizes_and_moving_reference_max(dev, parity, B, S, H, boo
     assert torch.isfinite(out.float()).all()
     parity.check(f"attention_edge[B={B},S={S},H={H},boost={boost_at}]", rel_err(out, ref)[0], default=2e-2,
                  note="torch SDPA fp32 on the same bf16 q,k,v")
+
+
+# ---------------------------------------------------------------------------------------------- CUDA-graph capture
+def test_full_step_is_cuda_graph_capture_safe(dev, golden_dir):
+    """"functions are re-entrant and capture-safe (no host sync, no allocation) so a whole denoising step can be
+    CUDA-graph captured".  One full guided step of a 2-layer LoRA + RoPE model — every launch of the transformer forward (text /
+    patch embedding, 2 x (AdaLN, LoRA-down, fused QKV + norm + RoPE, tcgen05 attention, out-proj, FFN), final norms, proj_out,
+    unpatchify) and the fused CFG + DDIM kernel — is captured into ONE graph through the ctypes C-ABI and replayed on new input
+    values: the replay must reproduce the eager step bit for bit."""
+    import s2v_b200
+    O = _O()
+    fx = torch.load(os.path.join(golden_dir, "transformer_tiny.pt"))["lora_rope"]
+    cfg = O.TransformerConfig(**fx["cfg"])
+    m = build_model(cfg, bf16_params(O.synth_params(cfg, seed=fx["seed"])), dev, True)
+    io = fx["io"]
+    rv, rr = O.pipeline_rope_tables(io["hidden"].shape[3] * 8, io["hidden"].shape[4] * 8, io["hidden"].shape[1])
+    rv, rr = tuple(t.to(dev) for t in rv), tuple(t.to(dev) for t in rr)
+    sched = s2v_b200.CogVideoXDDIMScheduler.for_cogvideox(1.0)
+    sched.set_timesteps(50)
+    t = sched._timesteps_host[3]
+    lat = io["hidden"][:1].to(BF16).to(dev).contiguous()             # static input buffers of the graph
+    ref, txt = io["ref"].to(BF16).to(dev), io["text"].to(BF16).to(dev)
+    tdev = torch.full((2,), float(t), device=dev)
+    model_in = torch.empty((2,) + tuple(lat.shape[1:]), device=dev, dtype=BF16)
+    nxt = torch.empty_like(lat)
+
+    def step():
+        model_in[:1].copy_(lat)
+        model_in[1:].copy_(lat)
+        noise = m(hidden_states=model_in, ref_img_states=ref, encoder_hidden_states=txt, timestep=tdev, image_rotary_emb=rv,
+                  ref_image_rotary_emb=rr, return_dict=False, eval=True)[0]
+        sched.step_cfg(noise, t, lat, 6.0, out=nxt)
+
+    from s2v_b200 import _lib
+    step()                                                            # warm-up: packs the weights, opts kernels in to their shared memory
+    torch.cuda.synchronize()
+    eager = nxt.clone()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    n0 = _lib.launch_count
+    with torch.cuda.stream(side), torch.cuda.graph(graph, stream=side):
+        step()
+    launches = _lib.launch_count - n0
+    torch.cuda.current_stream().wait_stream(side)
+    nxt.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert launches > 40, launches                                    # the whole step went through the C-ABI during capture
+    assert torch.equal(nxt, eager)
+    # new input values in the same buffers: replay == eager again
+    lat.copy_((lat.float() * 0.5 + 0.1).to(BF16))
+    graph.replay()
+    torch.cuda.synchronize()
+    replayed = nxt.clone()
+    step()
+    torch.cuda.synchronize()
+    assert torch.equal(replayed, nxt)
+
+
+# ---------------------------------------------------------------------------------------------- CTA-pair GEMM (cta_group::2)
+@pytest.mark.parametrize("M,N,K,r,epi", [(2048, 256, 64, 0, "bias"), (2049, 512, 3072, 0, "gelu"), (4000, 768, 256, 16, "bias"),
+                                        (2304, 3072, 1024, 128, "gate"), (2175, 264, 128, 8, "bias"), (38252, 256, 3072, 0, "bias")])
+def test_linear_cta_pair_tiles_vs_fp32_matmul(dev, parity, M, N, K, r, epi):
+    """Shapes that take the cta_group::2 path (M >= 2048, N >= 256: 256 x 256 tiles over two SMs): pair tiles whose second CTA is
+    partly or wholly beyond M, N that is not a multiple of the 256-wide tile (zero-filled B half), K of one block, every epilogue,
+    LoRA-B as extra K blocks — all rows against an fp32 matmul of the same bf16 operands."""
+    from s2v_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(BF16).to(dev)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(BF16).to(dev)
+    b = (0.1 * torch.randn(N, generator=g)).to(BF16).to(dev)
+    ref = x.float() @ w.float().t() + b.float()
+    kw = {}
+    if r:
+        a = (torch.randn(r, K, generator=g) / K ** 0.5).to(BF16).to(dev)
+        bb = (torch.randn(N, r, generator=g) / r ** 0.5).to(BF16).to(dev)
+        t = torch.empty(M, r, device=dev, dtype=BF16)
+        ops.linear(x, a, None, t, alpha=0.5)
+        ref = ref + t.float() @ bb.float().t()
+        kw.update(lora_t=t, lora_b=bb)
+    if epi == "gelu":
+        out = torch.empty(M, N, device=dev, dtype=BF16)
+        ops.linear(x, w, b, out, epilogue=ops.EPI_BIAS_GELU, **kw)
+        ref = F.gelu(ref, approximate="tanh")
+    elif epi == "gate":
+        rows_per_batch, text_len = M // 2, 100
+        mod = torch.randn(2, 2 * N, generator=g).to(dev)
+        res = torch.randn(M, N, generator=g).to(BF16).to(dev)
+        out = res.clone()
+        ops.linear(x, w, b, out, epilogue=ops.EPI_GATE_RESIDUAL, mod=mod, gate_off_text=0, gate_off_other=N, rows_per_batch=rows_per_batch,
+                   text_len=text_len, **kw)
+        rows = torch.arange(M, device=dev)
+        gate = torch.where(((rows % rows_per_batch) < text_len)[:, None], mod[rows // rows_per_batch, :N], mod[rows // rows_per_batch, N:])
+        ref = res.float() + gate * ref
+    else:
+        out = torch.empty(M, N, device=dev, dtype=BF16)
+        ops.linear(x, w, b, out, **kw)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    parity.check(f"linear_cta_pair[M={M},N={N},K={K},r={r},{epi}]", rel_err(out, ref)[0], default=5e-3, max_abs=rel_err(out, ref)[1],
+                 note="fp32 matmul on the same bf16 operands; all rows")

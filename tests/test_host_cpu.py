@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # ------------------------------------------------------------------ C ABI
 def _header_symbols():
     src = open(os.path.join(ROOT, "include", "s2v_b200.h")).read()
-    return sorted(set(re.findall(r"S2V_API\s+(?:const\s+char\*|int)\s+(s2v_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"S2V_API\s+(?:const\s+char\*|int64_t|int)\s+(s2v_\w+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -28,9 +28,22 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/s2v_b200.h but not exported"
     # and the Python binding knows every compute entry point
     for s in syms:
-        if s != "s2v_last_error":
+        if s not in ("s2v_last_error", "s2v_workspace_bytes"):     # the two entries that do not return an int status
             assert s in _lib.SIGNATURES, s
+    assert "s2v_workspace_bytes" in syms
     assert lib.s2v_abi_version() == 1
+
+
+def test_workspace_bytes_query():
+    """SURVEY §8b `s2v_workspace_bytes`: host-only arithmetic, usable without a GPU; the cfg-3 geometry needs ~2.6 GB."""
+    lib = _lib.load()
+    B, S, D = 2, 19126, 3072
+    got = lib.s2v_workspace_bytes(B, S, D, 4 * D, 3 * 128, 85)
+    up = lambda b: (b + 255) // 256 * 256  # noqa: E731
+    rows = B * S
+    want = 3 * up(rows * D * 2) + up(rows * 3 * D * 2) + up(rows * 4 * D * 2) + up(rows * 384 * 2) + up(85 * B * 6 * D * 4)
+    assert got == want and 2.3e9 < got < 2.8e9
+    assert lib.s2v_workspace_bytes(0, S, D, 4 * D, 0, 1) < 0 and b"bad geometry" in lib.s2v_last_error()
 
 
 def test_linear_args_struct_matches_header_layout():

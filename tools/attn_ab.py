@@ -2,7 +2,7 @@
 next to torch SDPA (cuDNN / flash backend) on the same tensors as the library reference point.
 
     python tools/build_attn_exp.py            # here (cross-compile)
-    python tools/attn_ab.py [name=variant:poly:skew ...]      # on the GPU box; variant bit0 = HI warp numbering, bit1 = K/V multicast
+    python tools/attn_ab.py [name=variant:poly:skew ...]      # on the GPU box; variant bit0 = HI warp numbering, bit1 = K/V multicast, bit2 = 80-key tiles
 The order alternates between repetitions (thermal drift otherwise favours whoever runs first); medians are reported, and every
 variant's output is checked against the shipped kernel's (max abs difference) before it is timed."""
 import ctypes as C
@@ -27,7 +27,7 @@ vp, i32 = C.c_void_p, C.c_int32
 exp.s2v_attn_fwd_exp.argtypes = [vp, vp, i32, i32, i32, C.c_float, i32, i32, i32, vp, vp]
 exp.s2v_attn_fwd_exp.restype = C.c_int
 exp.s2v_last_error.restype = C.c_char_p
-dbg = torch.zeros(2, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(2 + 3 * 76 * 48 * 2, dtype=torch.int64, device="cuda")
 reps = int(os.environ.get("REPS", "6"))
 iters = int(os.environ.get("ITERS", "6"))
 
@@ -36,8 +36,9 @@ for a in sys.argv[1:]:
     name, spec = a.split("=")
     cfgs[name] = tuple(int(x) for x in spec.split(":"))
 if not cfgs:
-    cfgs = {"r1_lo": (0, 1, 200), "hi": (1, 1, 200), "mc": (2, 1, 200), "hi_mc": (3, 1, 200), "hi_p0": (1, 0, 200), "hi_mc_p2": (3, 2, 200),
-            "hi_s0": (1, 1, 0)}
+    cfgs = {"r1_lo": (0, 1, 200), "hi_mc": (3, 1, 200), "bk80": (4, 1, 200), "bk80_hi": (5, 1, 200), "bk80_mc": (6, 1, 200),
+            "bk80_hi_mc": (7, 1, 200), "bk80_hi_mc_p0": (7, 0, 200), "bk80_hi_mc_p2": (7, 2, 200), "bk80_hi_mc_s0": (7, 1, 0),
+            "bk80_hi_mc_s400": (7, 1, 400)}
 
 
 def run_exp(c, o):
@@ -70,7 +71,7 @@ def timed(fn, c):
         fn(c, out)
     e1.record()
     torch.cuda.synchronize()
-    cyc, ns = (int(x) for x in dbg.tolist())
+    cyc, ns = (int(x) for x in dbg[:2].tolist())
     return e0.elapsed_time(e1) / iters, (cyc / ns * 1e3 if ns else 0.0)
 
 

@@ -16,9 +16,10 @@ OUT = os.path.join(ROOT, "tools", "bin", "libattn_exp.so")
 def build():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     objs = []
-    for name, extra in (("attn_tcgen05", ["-DS2V_ATTN_EXPERIMENT"]), ("host_util", [])):
+    for src_dir, name, extra in ((b.CSRC, "attn_tcgen05", ["-DS2V_ATTN_EXPERIMENT"]), (b.CSRC, "host_util", []),
+                                 (os.path.join(ROOT, "tools"), "clock_probe", [])):
         obj = os.path.join(ROOT, "tools", "bin", name + "_exp.o")
-        subprocess.run([b._nvcc(), *b.NVCC_FLAGS, *extra, "-c", os.path.join(b.CSRC, name + ".cu"), "-o", obj], check=True)
+        subprocess.run([b._nvcc(), *b.NVCC_FLAGS, *extra, "-c", os.path.join(src_dir, name + ".cu"), "-o", obj], check=True)
         objs.append(obj)
     subprocess.run([b._nvcc(), "-shared", "-o", OUT, *objs, "-lcudart"], check=True)
     return OUT

@@ -47,7 +47,7 @@ for name in only:
         ms.append(e0.elapsed_time(e1))
     fl = 2.0 * M * N * (K + r)
     best = min(ms[1:])
-    print(json.dumps({"gemm": name, "group_m": os.environ.get("S2V_GEMM_GROUP_M", "default"), "l2_hint": os.environ.get("S2V_GEMM_L2_HINT", "default"), "M": M, "N": N, "K": K, "ms": round(best, 4),
+    print(json.dumps({"gemm": name, "group_m": os.environ.get("S2V_GEMM_GROUP_M", "default"), "M": M, "N": N, "K": K, "ms": round(best, 4),
                       "tflops": round(fl / best / 1e9, 1), "algorithmic_read_MB": round((M * K + N * K + M * groups * r + N * r) * 2 / 1e6, 1),
                       "algorithmic_write_MB": round(M * N * 2 / 1e6, 1)}), flush=True)
     del w, out

@@ -51,7 +51,7 @@ exp = C.CDLL(os.path.join(ROOT, "tools", "bin", "libattn_exp.so"))   # python to
 exp.s2v_attn_fwd_exp.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p]
 exp.s2v_attn_fwd_exp.restype = C.c_int
-dbg = torch.zeros(2, dtype=torch.int64, device=dev)
+dbg = torch.zeros(2 + 3 * 76 * 48 * 2, dtype=torch.int64, device=dev)   # sums + one (start ns, end ns, cycles) record per CTA
 CUR = [0, 1, 200]
 shipped_attention = ops.attention
 
@@ -70,7 +70,7 @@ for a in sys.argv[1:]:   # name=variant:poly:skew   (variant bit 0 = HI warp num
     name, spec = a.split("=")
     configs[name] = None if spec == "shipped" else tuple(int(x) for x in spec.split(":"))
 if not configs:
-    configs = {"shipped": None, "r1_lo": (0, 1, 200), "hi": (1, 1, 200), "mc": (2, 1, 200), "hi_mc": (3, 1, 200)}
+    configs = {"shipped": None, "r1_lo": (0, 1, 200), "hi_mc": (3, 1, 200), "bk80": (4, 1, 200), "bk80_hi_mc": (7, 1, 200)}
 steps = int(os.environ.get("STEPS", "2"))
 run(2)  # warm up (clocks settle on the power cap)
 res = {k: [] for k in configs}
@@ -85,8 +85,19 @@ for rep in range(int(os.environ.get("REPS", "2"))):
         s2v_b200.engine.ops.attention = ops.attention
         dbg.zero_()
         r = run(steps)
-        cyc, ns = [int(x) for x in dbg.tolist()]
-        res[k].append(r + ((round(cyc / max(ns, 1) * 1e3), round(cyc / (steps * 42 * 7200) / 299)) if c is not None else ()))   # + (attention SM MHz, cycles per 64-key step)
+        cyc, ns = [int(x) for x in dbg[:2].tolist()]
+        extra = ()
+        if c is not None:
+            # SM clock through the LAST attention launch of the run: CTAs sorted by start time, 8 equal-count bins
+            rec = dbg[2:].view(-1, 3).cpu()
+            rec = rec[rec[:, 2] > 0]
+            rec = rec[rec[:, 0].argsort()]
+            t0 = int(rec[0, 0])
+            bins = []
+            for ch in rec.chunk(8):
+                bins.append((round(float((ch[:, 0].float().mean() - t0)) / 1e6, 2), round(float(ch[:, 2].double().sum() / (ch[:, 1] - ch[:, 0]).double().sum() * 1e3))))
+            extra = (round(cyc / max(ns, 1) * 1e3), round(cyc / (steps * 42 * 7200) / 299), {"clock_mhz_through_last_launch(ms,mhz)": bins})
+        res[k].append(r + extra)   # + (attention SM MHz, cycles per 64-key step, clock trajectory)
 ops.attention = shipped_attention
 for k, v in res.items():
     print(json.dumps({"config": k, "spec": configs[k], "attn_ms, step_ms, attn_sm_mhz, cycles_per_step": v}), flush=True)
