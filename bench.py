@@ -100,6 +100,24 @@ def ncu_traffic(workload):
     return (d["dram_bytes"], d["source"]) if d else (None, None)
 
 
+class EnergyMeter:
+    """Board energy over an interval from NVML's cumulative counter (nvmlDeviceGetTotalEnergyConsumption, millijoules)."""
+
+    def __init__(self, index):
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.read()
+        except Exception:
+            self.h = None
+
+    def read(self):
+        return self.nv.nvmlDeviceGetTotalEnergyConsumption(self.h) / 1e3 if self.h is not None else None
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -251,12 +269,16 @@ def run_product(args, w):
             return float(t.item())
         return ms
 
-    def timed_loop(wl, inp, sp, P_total, steps, warmup, host_io=False, timer=None):
+    meter = EnergyMeter(local) if rank == 0 else None
+    energy = {}
+
+    def timed_loop(wl, inp, sp, P_total, steps, warmup, host_io=False, timer=None, energy_key=None):
         """W untimed + K timed guided steps of this rank's prompts, then the path's single collective; device time, max over ranks."""
         lat = call(wl, inp.lat_d, inp.pos_d, inp.neg_d, inp.ref_d, window(0, warmup)) if warmup else inp.lat_d
         sync_all()
         ops.set_kernel_timer(timer)
         launches0 = _lib.launch_count
+        j0 = meter.read() if (meter and energy_key) else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.nvtx.range_push("timed")   # `ncu --nvtx --nvtx-include timed/` captures exactly the timed launches
         e0.record()
@@ -272,6 +294,8 @@ def run_product(args, w):
         e1.record()
         torch.cuda.nvtx.range_pop()
         sync_all()
+        if j0 is not None:
+            energy[energy_key] = (meter.read() - j0) / steps
         ops.set_kernel_timer(None)
         ms = max_over_ranks(e0.elapsed_time(e1))
         assert torch.isfinite(gathered.float()).all(), "non-finite latents"
@@ -285,7 +309,7 @@ def run_product(args, w):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, launches, lat_final = timed_loop(w, inp, sp, P_total, args.steps, args.warmup)
+    ms, launches, lat_final = timed_loop(w, inp, sp, P_total, args.steps, args.warmup, energy_key="value_loop")
     clocks = sampler.stop() if rank == 0 else None
     # second pass of the same steps with CUDA events around the five big kernels (rank 0 only records)
     names = ["s2v_attn_fwd", "s2v_qkv_lora", "s2v_outproj_lora_gate_residual", "s2v_ffn_up_gelu_lora", "s2v_ffn_down_lora_gate_residual"]
@@ -337,6 +361,9 @@ def run_product(args, w):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config_of(args, w, P_total),
             "clocks": clocks,
+            "energy": {"joule_per_step_gpu0": round(energy["value_loop"], 1) if energy.get("value_loop") else None,
+                       "mean_power_w": round(energy["value_loop"] / (ms / args.steps / 1e3), 1) if energy.get("value_loop") else None,
+                       "source": "nvmlDeviceGetTotalEnergyConsumption around the timed loop (rank 0's GPU)"},
             "e2e": {"value": round(e2e_v, 4), "unit": "steps/s", "h2d_bytes_per_step": inp.h2d_bytes, "d2h_bytes_per_step": inp.d2h_bytes,
                     "ms_per_step": round(ms_e2e / args.steps, 3),
                     "api": "CustomCogVideoXPipeline.__call__ once per step with pinned host tensors (latents, prompt embeddings, reference latents in; latents out)"},

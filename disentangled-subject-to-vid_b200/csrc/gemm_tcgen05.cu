@@ -640,6 +640,14 @@ static bool use_cta_pairs(int M, int N) {
     return M >= 2048 && N >= 256;
 }
 
+// Persistent CTAs (SMs) a projection GEMM occupies.  S2V_GEMM_SMS overrides for the power-density experiments of
+// profiles/r02_summary.md ("the board's power governor"): fewer SMs = lower instantaneous power at a given clock.
+static int gemm_sms() {
+    static const int forced = [] { const char* e = getenv("S2V_GEMM_SMS"); return e ? atoi(e) : 0; }();
+    const int n = sm_count();
+    return (forced > 0 && forced < n) ? forced : n;
+}
+
 template <int BN, int EPI, bool TWO = false>
 static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const ConvExtra* conv = nullptr, const s2v_qk_norm_args* qk = nullptr) {
     using Cfg = GemmCfg<BN, TWO>;
@@ -690,7 +698,8 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
     const int num_tiles = TR ? (a->M + BN - 1) / BN : ((a->M + TILE_M - 1) / TILE_M) * ((a->N + BN - 1) / BN);
     if (TWO) {
         if (p.group_m > 1) p.group_m = (p.group_m + 1) / 2;      // group height is counted in tiles (256-row pair-blocks here)
-        const int clusters = num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2;
+        const int sms = conv ? sm_count() : gemm_sms();
+        const int clusters = num_tiles < sms / 2 ? num_tiles : sms / 2;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * clusters);
         cfg.blockDim = dim3(GEMM_THREADS);
@@ -707,7 +716,8 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
         if (e != cudaSuccess) return set_cuda_error(e, "gemm_tcgen05_kernel(cta pair)");
         return check_launch("gemm_tcgen05_kernel(cta pair)");
     }
-    const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+    const int sms1 = conv ? sm_count() : gemm_sms();
+    const int grid = num_tiles < sms1 ? num_tiles : sms1;
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
     return check_launch("gemm_tcgen05_kernel");
 }

@@ -21,6 +21,10 @@ __global__ void clock_probe_kernel(unsigned long long* __restrict__ buf, int n, 
 }
 
 extern "C" __attribute__((visibility("default"))) int s2v_clock_probe(void* buf_u64x2, int32_t n, uint32_t period_ns, void* stop_flag, void* stream) {
+    // An SM keeps the L1 / shared-memory split of the blocks resident on it: with the default (small) carve-out of this kernel its SM
+    // could not take a 200 KB GEMM / attention block while the probe runs (measured: persistent GEMMs ran on 147 SMs + a straggler
+    // and took twice as long).  Ask for the maximum shared-memory carve-out so that the probe's SM stays usable.
+    cudaFuncSetAttribute(clock_probe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     clock_probe_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned long long*>(buf_u64x2), n, period_ns,
                                                                        static_cast<volatile int*>(stop_flag));
     return (int)cudaPeekAtLastError();

@@ -24,6 +24,7 @@ model, _ = bench.build_model(w, dev)
 n, F, S, D = bench.geometry(w)
 sched = s2v_b200.CogVideoXDDIMScheduler.for_cogvideox(1.0)
 sched.set_timesteps(50)
+ALL_STEPS = list(sched._timesteps_host)   # the pipeline call below installs its own (shorter) list on the scheduler
 pipe = s2v_b200.CustomCogVideoXPipeline(None, None, model, None, sched)
 inp = bench.Inputs(w, 1, dev, 0, 4096)
 exp = C.CDLL(os.path.join(ROOT, "tools", "bin", "libattn_exp.so"))
@@ -31,7 +32,7 @@ exp.s2v_clock_probe.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C
 
 
 def steps(k, first=0):
-    ts = [sched._timesteps_host[(first + i) % 50] for i in range(k)]
+    ts = [ALL_STEPS[(first + i) % 50] for i in range(k)]
     return pipe(prompt=None, prompt_embeds=inp.pos_d, negative_prompt_embeds=inp.neg_d, ref_img_states=inp.ref_d, latents=inp.lat_d, height=480,
                 width=720, num_frames=49, num_inference_steps=50, timesteps=ts, guidance_scale=6.0, output_type="latent", return_dict=False)[0]
 

@@ -55,7 +55,27 @@ for P in (1, 2):
     sharded = parallel.sharded_denoise(parallel.plan(P, world, rank), P, lat, pe, ref, steps, model_fn, step_fn, lambda i: 6.0)
     torch.cuda.synchronize()
     results[f"P{P}_{parallel.plan(P, world, rank).mode}"] = bool(torch.equal(single, sharded))
-ok = torch.tensor([int(all(results.values()))], device=dev)
+# ---- the public call in CFG-parallel mode (pipe.enable_cfg_parallel): every rank pair owns world/2 ... prompts, one CFG half per GPU
+if world % 2 == 0:
+    pairs = world // 2
+    spc = parallel.plan(pairs, world, rank, mode="cfg")
+    gp = torch.Generator().manual_seed(50 + rank // 2)                   # both ranks of a pair draw the same prompt
+    lat = torch.randn(1, Fr, 16, h, w, generator=gp).to(bf16).to(dev)
+    pos = (0.2 * torch.randn(1, 226, 64, generator=gp)).to(bf16).to(dev)
+    neg = (0.2 * torch.randn(1, 226, 64, generator=gp)).to(bf16).to(dev)
+    ref = (0.7 * torch.randn(1, 1, 16, h, w, generator=gp)).to(bf16).to(dev)
+    kw = dict(prompt_embeds=pos, negative_prompt_embeds=neg, ref_img_states=ref, latents=lat, height=h * 8, width=w * 8, num_frames=(Fr - 1) * 4 + 1,
+              num_inference_steps=4, guidance_scale=6.0, use_dynamic_cfg=True, output_type="latent", return_dict=False)
+    single = pipe(**kw)[0].clone()
+    pipe.enable_cfg_parallel(spc, record_times=True)
+    sharded = pipe(**kw)[0].clone()
+    xt = pipe._cfg_xchg.times_ms()
+    pipe.disable_cfg_parallel()
+    results["pipe_call_cfg_parallel"] = bool(torch.equal(single, sharded))
+    gathered = parallel.gather_latents(sharded, pairs, spc)
+    results["gather_in_prompt_order"] = bool(gathered.shape[0] == pairs and torch.equal(gathered[rank // 2], sharded[0]))
+    results["pair_exchange_ms_median"] = sorted(xt)[len(xt) // 2]
+ok = torch.tensor([int(all(bool(v) for v in results.values()))], device=dev)
 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(json.dumps({"world": world, "bit_identical_to_single_gpu": results, "all_ranks_ok": bool(ok.item())}))
