@@ -750,3 +750,37 @@ def test_linear_cta_pair_tiles_vs_fp32_matmul(dev, parity, M, N, K, r, epi):
     assert torch.isfinite(out.float()).all()
     parity.check(f"linear_cta_pair[M={M},N={N},K={K},r={r},{epi}]", rel_err(out, ref)[0], default=5e-3, max_abs=rel_err(out, ref)[1],
                  note="fp32 matmul on the same bf16 operands; all rows")
+
+
+# ---------------------------------------------------------------------------------------------- float16 models (CogVideoX-2B)
+def test_fp16_model_runs_in_bf16_and_returns_fp16(dev, golden_dir, parity):
+    """S/inference.py:191,210 loads CogVideoX-2B with torch_dtype=float16.  The engine has no fp16 arithmetic: fp16 parameters are
+    packed as bf16 copies (one rounding, with a warning), the forward computes in bf16 and hands fp16 back.  The deviation from the
+    reference's fp16 arithmetic is therefore bf16-sized (8 significand bits instead of 11) — recorded here, against the fp32 oracle
+    on the same fp16 weights, next to the error of the oracle executed in fp16."""
+    import warnings
+    import s2v_b200
+    from s2v_b200 import engine
+    O = _O()
+    fx = torch.load(os.path.join(golden_dir, "transformer_tiny.pt"))["plain_sincos"]       # 2B semantics: no RoPE, sincos positions, no LoRA
+    cfg = O.TransformerConfig(**fx["cfg"])
+    p16 = {k: v.half() for k, v in O.synth_params(cfg, seed=fx["seed"]).items()}
+    m = s2v_b200.CogVideoXTransformer3DModel(
+        num_attention_heads=cfg.num_attention_heads, num_layers=cfg.num_layers, time_embed_dim=cfg.time_embed_dim,
+        text_embed_dim=cfg.text_embed_dim, use_rotary_positional_embeddings=False).half()
+    load_flat_params(m, p16)
+    m = m.to(dev)
+    io = fx["io"]
+    hid, ref, txt = io["hidden"].half(), io["ref"].half(), io["text"].half()
+    engine._FP16_WARNED = False
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        got = m(hidden_states=hid.to(dev), ref_img_states=ref.to(dev), encoder_hidden_states=txt.to(dev), timestep=io["timestep"].to(dev),
+                return_dict=False, eval=True)[0]
+    assert any("float16" in str(w_.message) for w_ in wlist)
+    assert got.dtype == torch.float16 and got.shape == fx["out"].shape
+    exact = O.transformer_forward(up(p16), cfg, hid.float(), ref.float(), txt.float(), io["timestep"], None, None, eval=True)
+    ref16 = O.transformer_forward(p16, cfg, hid, ref, txt, io["timestep"], None, None, eval=True)
+    parity.check("transformer_tiny_fp16_model[plain_sincos]", rel_err(got, exact)[0], ref=rel_err(ref16, exact)[0], default=1e-2,
+                 max_abs=rel_err(got, exact)[1], ref_max_abs=rel_err(ref16, exact)[1],
+                 note="fp16 weights run through the bf16 engine; yardstick = the oracle executed in fp16 (the reference's 2B dtype)")

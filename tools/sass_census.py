@@ -1,0 +1,54 @@
+"""SASS opcode census of libs2v_b200.so: per kernel, how many tcgen05 / TMEM / TMA instructions the shipped binary contains
+(B200_PROFILING.md "What proves a Blackwell-native kernel": tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG/UTMASTG,
+legacy mma.sync -> HMMA).  Run here (no GPU): python tools/sass_census.py > profiles/r02_sass_census.md"""
+import collections
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "disentangled-subject-to-vid_b200", "libs2v_b200.so")
+sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+OPS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTCBAR.2CTA.MULTICAST", "SYNCS", "MUFU.EX2", "FFMA2", "FADD2", "F2FP", "HMMA",
+       "UCGABAR", "USETMAXREG", "ELECT"]
+per = collections.OrderedDict()
+cur = None
+for line in sass.splitlines():
+    m = re.search(r"Function : (\S+)", line)
+    if m:
+        cur = m.group(1)
+        per[cur] = collections.Counter()
+        continue
+    m = re.search(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    if m and cur:
+        op = m.group(1)
+        per[cur]["_total"] += 1
+        for o in OPS:
+            if op == o or op.startswith(o + "."):
+                per[cur][o] += 1
+        if op.startswith("UTCHMMA") and ".2CTA" in op:
+            per[cur]["UTCHMMA.2CTA"] += 0   # counted by the prefix rule above
+        if op.startswith("UTMALDG") and "MULTICAST" in op:
+            per[cur]["UTMALDG(multicast)"] += 1
+demangled = dict(zip(per.keys(), subprocess.run(["c++filt"], input="\n".join(per.keys()), capture_output=True, text=True).stdout.splitlines()))
+cols = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMALDG(multicast)", "UTMASTG", "UTCBAR", "SYNCS", "MUFU.EX2", "FFMA2", "FADD2", "F2FP", "HMMA", "UCGABAR"]
+print(f"# SASS opcode census of `{os.path.relpath(lib, ROOT)}` (cuobjdump -sass, sm_100a)\n")
+print("`UTCHMMA` = tcgen05.mma (`.2CTA` = cta_group::2), `LDTM`/`STTM` = tcgen05.ld/st, `UTMALDG` = cp.async.bulk.tensor loads (TMA), `UTCBAR` = tcgen05.commit,")
+print("`SYNCS` = mbarrier ops, `UCGABAR` = cluster barrier, `HMMA` = legacy mma.sync (none expected).  Kernels without tensor-core / TMA work (elementwise,")
+print("GroupNorm, scheduler ...) are listed at the end by name only.\n")
+print("| kernel | instr | " + " | ".join(cols) + " |")
+print("|---|---|" + "---|" * len(cols))
+plain = []
+for k, c in per.items():
+    name = re.sub(r"\(.*", "", demangled.get(k, k)).replace("void ", "").replace("s2v::", "")
+    if not any(c[o] for o in ("UTCHMMA", "LDTM", "UTMALDG")):
+        plain.append(name)
+        continue
+    print(f"| `{name}` | {c['_total']} | " + " | ".join(str(c[o]) for o in cols) + " |")
+print("\nOther kernels (no tcgen05 / TMA instructions): " + ", ".join(f"`{n}`" for n in sorted(set(plain))))
+tot = collections.Counter()
+for c in per.values():
+    tot.update(c)
+print(f"\nTotals: UTCHMMA {tot['UTCHMMA']} (of which .2CTA {tot['UTCHMMA.2CTA']}), LDTM {tot['LDTM']}, STTM {tot['STTM']}, UTMALDG {tot['UTMALDG']} "
+      f"(multicast {tot['UTMALDG(multicast)']}), HMMA {tot['HMMA']}.")
