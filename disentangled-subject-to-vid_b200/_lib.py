@@ -82,6 +82,8 @@ SIGNATURES = {
     "s2v_ddim_step": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp],
     "s2v_dpm_step": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp],
     "s2v_conv_gemm": [C.POINTER(ConvArgs), _vp],
+    "s2v_conv_gemm_stats": [C.POINTER(ConvArgs), _vp, C.POINTER(C.c_int32), _vp],
+    "s2v_vae_groupnorm_finalize": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_vae_latent_rows": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_vae_latent_im2col": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_vae_groupnorm_stats": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],

@@ -2,6 +2,7 @@
 // small-batch linears (timestep MLP / modulation vectors), patchify / unpatchify, CFG + DDIM update.
 // All are coalesced 16-byte vector kernels with warp-shuffle reductions; statistics and arithmetic in fp32.
 #include <math.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -187,6 +188,124 @@ adaln_modulate_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, const 
             orow[vi] = pack8(o);
         }
         asm volatile("" ::: "memory");   // keep the parameter loads of later vectors from being hoisted (register pressure -> spills)
+    }
+}
+
+// Two rows per warp (round 2).  Per 16-byte vector of a row the single-row kernel also fetches 16 B of ln_w, 16 B of ln_b, 32 B of scale
+// and 32 B of shift through L1: 96 B of parameter reads per 16 B of activations, i.e. ~155 B/clk/SM at the HBM rate — more than
+// the 128 B/clk an SM's L1 delivers, which is what held the kernel at 0.59 of the copy bandwidth.  Two consecutive rows share one
+// fetch of every parameter vector (rows of one batch and one segment share scale / shift too; the pair that straddles a
+// text | other or batch boundary fetches its own).  Each row's arithmetic is exactly the single-row kernel's (bit-identical results).
+template <int MAXV>
+__global__ void __launch_bounds__(128, 3)      // 170 registers: two packed rows of up to 4096 elements without spills; 12 warps = 24 rows per SM
+adaln_modulate2_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, const bf16* __restrict__ ln_w,
+                       const bf16* __restrict__ ln_b, const float* __restrict__ mod, int mod_stride, int shift_off_text,
+                       int scale_off_text, int shift_off_other, int scale_off_other, long long rows, int S, int D,
+                       int text_len, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row0 = ((long long)blockIdx.x * 4 + (threadIdx.x >> 5)) * 2;
+    if (row0 >= rows) return;
+    const bool has1 = row0 + 1 < rows;
+    const int nvec = D / 8;
+    uint4 ra[MAXV], rb[MAXV];
+    const uint4* xa = reinterpret_cast<const uint4*>(x + row0 * D);
+    const uint4* xb = xa + nvec;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const bool in = i * 32 + lane < nvec;
+        ra[i] = in ? __ldg(xa + i * 32 + lane) : make_uint4(0u, 0u, 0u, 0u);
+        rb[i] = (in && has1) ? __ldg(xb + i * 32 + lane) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        float f[8], g[8];
+        unpack8(ra[i], f);
+        unpack8(rb[i], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sa += f[j];
+            sb += g[j];
+        }
+    }
+    const float mean_a = warp_sum(sa) / float(D), mean_b = warp_sum(sb) / float(D);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        asm volatile("" : "+r"(ra[i].x), "+r"(ra[i].y), "+r"(ra[i].z), "+r"(ra[i].w));
+        asm volatile("" : "+r"(rb[i].x), "+r"(rb[i].y), "+r"(rb[i].z), "+r"(rb[i].w));
+    }
+    float qa = 0.f, qb = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        if (i * 32 + lane < nvec) {
+            float f[8], g[8];
+            unpack8(ra[i], f);
+            unpack8(rb[i], g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float da = f[j] - mean_a, db = g[j] - mean_b;
+                qa += da * da;
+                qb += db * db;
+            }
+        }
+    }
+    const float rstd_a = rsqrtf(warp_sum(qa) / float(D) + eps), rstd_b = rsqrtf(warp_sum(qb) / float(D) + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        asm volatile("" : "+r"(ra[i].x), "+r"(ra[i].y), "+r"(ra[i].z), "+r"(ra[i].w));
+        asm volatile("" : "+r"(rb[i].x), "+r"(rb[i].y), "+r"(rb[i].z), "+r"(rb[i].w));
+    }
+    const int ba = int(row0 / S), sa_ = int(row0 - (long long)ba * S);
+    const long long row1 = has1 ? row0 + 1 : row0;
+    const int bb = int(row1 / S), sb_ = int(row1 - (long long)bb * S);
+    const float* ma = mod + (long long)ba * mod_stride;
+    const float* mb = mod + (long long)bb * mod_stride;
+    const float* shift_a = ma + (sa_ < text_len ? shift_off_text : shift_off_other);
+    const float* scale_a = ma + (sa_ < text_len ? scale_off_text : scale_off_other);
+    const float* shift_b = mb + (sb_ < text_len ? shift_off_text : shift_off_other);
+    const float* scale_b = mb + (sb_ < text_len ? scale_off_text : scale_off_other);
+    const bool same = (shift_a == shift_b) && (scale_a == scale_b);      // warp-uniform
+    uint4* oa = reinterpret_cast<uint4*>(out + row0 * D);
+    uint4* ob = oa + nvec;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = i * 32 + lane;
+        if (vi < nvec) {
+            float f[8], g[8], wf[8], bfv[8];
+            unpack8(ra[i], f);
+            unpack8(rb[i], g);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(ln_w) + vi), wf);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(ln_b) + vi), bfv);
+            float4 s0 = __ldg(reinterpret_cast<const float4*>(scale_a) + 2 * vi), s1 = __ldg(reinterpret_cast<const float4*>(scale_a) + 2 * vi + 1);
+            float4 h0 = __ldg(reinterpret_cast<const float4*>(shift_a) + 2 * vi), h1 = __ldg(reinterpret_cast<const float4*>(shift_a) + 2 * vi + 1);
+            {
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float y = (f[j] - mean_a) * rstd_a * wf[j] + bfv[j];
+                    o[j] = y * (1.0f + sc[j]) + sh[j];
+                }
+                oa[vi] = pack8(o);
+            }
+            if (has1) {
+                if (!same) {
+                    s0 = __ldg(reinterpret_cast<const float4*>(scale_b) + 2 * vi); s1 = __ldg(reinterpret_cast<const float4*>(scale_b) + 2 * vi + 1);
+                    h0 = __ldg(reinterpret_cast<const float4*>(shift_b) + 2 * vi); h1 = __ldg(reinterpret_cast<const float4*>(shift_b) + 2 * vi + 1);
+                }
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float y = (g[j] - mean_b) * rstd_b * wf[j] + bfv[j];
+                    o[j] = y * (1.0f + sc[j]) + sh[j];
+                }
+                ob[vi] = pack8(o);
+            }
+        }
+        asm volatile("" ::: "memory");
     }
 }
 
@@ -486,6 +605,18 @@ extern "C" int s2v_adaln_modulate(const void* x, void* out, const void* ln_w, co
         return set_error(S2V_E_BADARG, "s2v_adaln_modulate: modulation offsets must be multiples of 4 floats");
     S2V_PROLOGUE();
     const long long rows = (long long)B * S;
+    // two rows per warp (see adaln_modulate2_kernel); S2V_ADALN_ROWS=1 keeps the single-row kernel (A/B, bit-identical)
+    static const bool two_rows = [] { const char* e = getenv("S2V_ADALN_ROWS"); return !(e && e[0] == '1'); }();
+    if (two_rows && D >= 1024) {
+        const unsigned grid2 = (unsigned)((rows + 7) / 8);
+        return dispatch_maxv(D, [&](auto mv) {
+            adaln_modulate2_kernel<decltype(mv)::value><<<grid2, 128, 0, stream>>>(
+                static_cast<const bf16*>(x), static_cast<bf16*>(out), static_cast<const bf16*>(ln_w),
+                static_cast<const bf16*>(ln_b), mod, mod_stride, shift_off_text, scale_off_text, shift_off_other,
+                scale_off_other, rows, S, D, text_len, eps);
+            return check_launch("adaln_modulate2_kernel");
+        });
+    }
     const unsigned grid = (unsigned)((rows + 7) / 8);
     return dispatch_maxv(D, [&](auto mv) {
         adaln_modulate_kernel<decltype(mv)::value><<<grid, 256, 0, stream>>>(

@@ -37,6 +37,9 @@ struct GemmKParams {
     int tap_off[27];
     const bf16* res;
     long long ldres;
+    // GroupNorm statistics of the convolution's OUTPUT, fused into the epilogue (S2V_EPI_CONV / S2V_EPI_CONV_T): per row-block partial
+    // sums [num_row_blocks, N, 2] (sum, sum of squares of the bf16-rounded values that are stored; the zero border ring adds nothing)
+    float* stats;
     // fused q/k LayerNorm + RoPE (S2V_EPI_QKV_NORM_ROPE): columns [0, qk_cols) are 64-wide q then k head vectors
     const bf16 *nq_w, *nq_b, *nk_w, *nk_b;
     const float *rope_cos, *rope_sin;
@@ -110,7 +113,8 @@ struct GemmCfg {
     static constexpr uint32_t B_BYTES = (TWO ? BN / 2 : BN) * GEMM_BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t STATS_BYTES = 2 * 4 * BN * 2 * 4;   // conv epilogue: 2 buffers x 4 warps x BN columns x (sum, sumsq) fp32
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STATS_BYTES;
 };
 
 // Tiles are walked group by group: a group is `group_m` consecutive row-blocks x ALL column-blocks, row-block fastest.  While a
@@ -141,6 +145,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* stat_red = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // [2][4][BN][2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -312,6 +317,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int pos0 = m_blk * TILE_M;
                 const int rem = pos0 % (p.Hp * p.Wp);
                 int hp = rem / p.Wp, wp = rem - hp * p.Wp;
+                float st_s = 0.f, st_q = 0.f;     // this channel's sum / sum of squares over the tile's positions (p.stats)
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     uint32_t v[32];
@@ -343,13 +349,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             f += bs;
                             f += rv[j];
                             if (brd) f = 0.f;
-                            p.out[(long long)(pos + p.out_row0) * p.ldo + ch] = __float2bfloat16(f);
+                            const bf16 fo = __float2bfloat16(f);
+                            p.out[(long long)(pos + p.out_row0) * p.ldo + ch] = fo;
+                            const float fr = __bfloat162float(fo);
+                            st_s += fr;
+                            st_q = fmaf(fr, fr, st_q);
                         }
                         if (++wp == p.Wp) {
                             wp = 0;
                             if (++hp == p.Hp) hp = 0;
                         }
                     }
+                }
+                if (p.stats && ch_ok) {
+                    p.stats[((long long)m_blk * p.N + ch) * 2] = st_s;
+                    p.stats[((long long)m_blk * p.N + ch) * 2 + 1] = st_q;
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -531,6 +545,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c * 32, v);
                 tmem_ld_wait();
                 const int col0 = n0 + c * 32;
+                float sv[32];      // S2V_EPI_CONV with p.stats: the bf16-rounded values this lane stores (0 where it stores nothing)
+                if (EPI == S2V_EPI_CONV) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sv[j] = 0.f;
+                }
                 if (row_ok && col0 < p.N) {
 #pragma unroll
                     for (int g8 = 0; g8 < 4; ++g8) {
@@ -585,7 +604,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             o.z = pack_bf16x2(f[4], f[5]);
                             o.w = pack_bf16x2(f[6], f[7]);
                             *reinterpret_cast<uint4*>(orow + c * 32 + g8 * 8) = o;
+                            if (EPI == S2V_EPI_CONV) {
+                                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    sv[g8 * 8 + 2 * j] = bf16_lo(ow[j]);
+                                    sv[g8 * 8 + 2 * j + 1] = bf16_hi(ow[j]);
+                                }
+                            }
                         }
+                    }
+                }
+                if (EPI == S2V_EPI_CONV && p.stats) {
+                    // column sums over this warp's 32 rows by a butterfly transpose-reduce: after the step with distance s a lane
+                    // keeps s of its columns (the half its bit selects) plus the partner's partial sums for them — 31 shuffles per
+                    // quantity instead of 160 — and lane l ends up with column c*32 + l
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sq[j] = sv[j] * sv[j];
+#pragma unroll
+                    for (int sdist = 16; sdist >= 1; sdist >>= 1) {
+                        const bool upper = (lane & sdist) != 0;
+#pragma unroll
+                        for (int j = 0; j < sdist; ++j) {
+                            const float keep_s = upper ? sv[j + sdist] : sv[j], send_s = upper ? sv[j] : sv[j + sdist];
+                            const float keep_q = upper ? sq[j + sdist] : sq[j], send_q = upper ? sq[j] : sq[j + sdist];
+                            sv[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, sdist);
+                            sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, sdist);
+                        }
+                    }
+                    float* dst = stat_red + ((size_t(acc) * 4 + q) * BN + c * 32 + lane) * 2;
+                    dst[0] = sv[0];
+                    dst[1] = sq[0];
+                }
+            }
+            if (EPI == S2V_EPI_CONV && p.stats) {
+                // the four epilogue warps' partial sums -> one row-block entry, in a fixed order (deterministic); the buffer is
+                // double-buffered by accumulator parity, so one named barrier per tile is enough
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int col = (warp - 2) * 32 + lane; col < BN; col += 128) {
+                    if (n0 + col < p.N) {
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; ++w4) {
+                            const float* srcp = stat_red + ((size_t(acc) * 4 + w4) * BN + col) * 2;
+                            a0 += srcp[0];
+                            a1 += srcp[1];
+                        }
+                        p.stats[((long long)m_blk * p.N + n0 + col) * 2] = a0;
+                        p.stats[((long long)m_blk * p.N + n0 + col) * 2 + 1] = a1;
                     }
                 }
             }
@@ -613,6 +680,7 @@ struct ConvExtra {
     const int* tap_off;
     const void* res;
     long long ldres;
+    float* stats;
 };
 
 // Rasterisation group height (in 128-row blocks).  DRAM reads of a launch ~ |X| + |W| * num_m / group_m as long as the group's
@@ -678,7 +746,7 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
     p.mod_stride = a->mod_stride; p.gate_off_text = a->gate_off_text; p.gate_off_other = a->gate_off_other;
     p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : a->M; p.text_len = a->text_len;
     p.taps = 1; p.cin_blocks = (a->K + GEMM_BK - 1) / GEMM_BK; p.a_row0 = 0; p.out_row0 = 0; p.Hp = 1; p.Wp = 1;
-    p.res = nullptr; p.ldres = 0;
+    p.res = nullptr; p.ldres = 0; p.stats = nullptr;
     p.nq_w = p.nq_b = p.nk_w = p.nk_b = nullptr; p.rope_cos = p.rope_sin = nullptr; p.qk_cols = 0; p.qk_eps = 0.f;
     if (qk) {
         p.nq_w = static_cast<const bf16*>(qk->nq_w); p.nq_b = static_cast<const bf16*>(qk->nq_b);
@@ -688,7 +756,7 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
     }
     if (conv) {
         p.taps = conv->taps; p.cin_blocks = (conv->cin + GEMM_BK - 1) / GEMM_BK; p.a_row0 = conv->a_row0; p.out_row0 = conv->out_row0;
-        p.Hp = conv->Hp; p.Wp = conv->Wp; p.res = static_cast<const bf16*>(conv->res); p.ldres = conv->ldres;
+        p.Hp = conv->Hp; p.Wp = conv->Wp; p.res = static_cast<const bf16*>(conv->res); p.ldres = conv->ldres; p.stats = conv->stats;
         for (int i = 0; i < 27; ++i) p.tap_off[i] = i < conv->taps ? conv->tap_off[i] : 0;
     }
 
@@ -796,9 +864,12 @@ extern "C" int s2v_ffn_down_lora_gate_residual(const s2v_linear_args* a, void* s
 }
 
 // ------------------------------------------------------------------------------------------------ implicit-GEMM convolution
-extern "C" int s2v_conv_gemm(const s2v_conv_args* c, void* stream_) {
+extern "C" int s2v_conv_gemm(const s2v_conv_args* c, void* stream) { return s2v_conv_gemm_stats(c, nullptr, nullptr, stream); }
+
+extern "C" int s2v_conv_gemm_stats(const s2v_conv_args* c, float* stats_partial, int32_t* row_blocks, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!c || !c->x || !c->w || !c->out) return set_error(S2V_E_BADARG, "s2v_conv_gemm: null pointer");
+    if (stats_partial && !row_blocks) return set_error(S2V_E_BADARG, "s2v_conv_gemm_stats: row_blocks must be given with stats_partial");
     if (c->taps != 1 && c->taps != 9 && c->taps != 27) return set_error(S2V_E_BADARG, "s2v_conv_gemm: taps must be 1, 9 or 27");
     if (c->T <= 0 || c->Hp < 3 || c->Wp < 3 || c->cin <= 0 || c->cout <= 0) return set_error(S2V_E_BADARG, "s2v_conv_gemm: empty problem");
     if ((c->cin % 8) || (c->cout % 8) || (c->ldx % 8) || (c->ldo % 8) || (c->ldw % 8) || (c->res && (c->ldres % 8)))
@@ -828,10 +899,19 @@ extern "C" int s2v_conv_gemm(const s2v_conv_args* c, void* stream_) {
     ConvExtra ex;
     ex.taps = c->taps; ex.cin = c->cin; ex.a_row0 = (int)(c->t_pad * plane); ex.out_row0 = (int)(c->t_pad * plane);
     ex.Hp = c->Hp; ex.Wp = c->Wp; ex.a_rows = (long long)(c->T + c->t_pad) * plane; ex.tap_off = off; ex.res = c->res; ex.ldres = c->ldres;
-    if (c->cout >= 256) return launch_gemm<256, S2V_EPI_CONV>(&a, stream, &ex);
+    ex.stats = stats_partial;
+    if (row_blocks) *row_blocks = (int32_t)((M + 127) / 128);      // the swapped-operand form below overrides (256 positions per block)
+    if (c->cout >= 256) {
+        // CTA pairs (256 positions x 256 channels per tile) like the projections; S2V_GEMM_2CTA=0 keeps single CTAs
+        if (use_cta_pairs((int)M, c->cout)) return launch_gemm<256, S2V_EPI_CONV, true>(&a, stream, &ex);
+        return launch_gemm<256, S2V_EPI_CONV>(&a, stream, &ex);
+    }
     // Cout <= 128: one N block.  With a 3x3(x3) kernel the swapped form (weights on the M side,
     // 256 positions on the N side) halves the shared-memory operand traffic per flop; S2V_CONV_T=0 keeps the plain form (A/B).
     static const bool conv_t = [] { const char* e = getenv("S2V_CONV_T"); return !(e && e[0] == '0'); }();
-    if (conv_t && c->cout <= 128 && c->taps > 1) return launch_gemm<256, S2V_EPI_CONV_T>(&a, stream, &ex);
+    if (conv_t && c->cout <= 128 && c->taps > 1) {
+        if (row_blocks) *row_blocks = (int32_t)((M + 255) / 256);
+        return launch_gemm<256, S2V_EPI_CONV_T>(&a, stream, &ex);
+    }
     return launch_gemm<128, S2V_EPI_CONV>(&a, stream, &ex);
 }

@@ -18,6 +18,8 @@ There is no CPU / eager fallback: the modules only hold parameters.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 import types
@@ -169,6 +171,9 @@ class CogVideoXEncoder3D(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ engine
+# GroupNorm statistics of the decoder out of the producing convolution's epilogue (default); S2V_VAE_FUSED_GN=0 reads the volume with
+# s2v_vae_groupnorm_stats instead (round 1; the two agree to fp32 summation order)
+FUSED_GN_STATS = os.environ.get("S2V_VAE_FUSED_GN", "1") != "0"
 GN_BLOCKS = 1184   # stage-1 blocks of the GroupNorm statistics (8 per SM): 296 measured 26 % of the HBM copy bandwidth
 
 
@@ -316,7 +321,11 @@ class VaeDecoderEngine:
         return self._bufs[key]
 
     # ---- kernels
-    def _conv(self, cv: _Conv, x: torch.Tensor, out: torch.Tensor, T: int, H: int, W: int, res: Optional[torch.Tensor] = None):
+    def _conv(self, cv: _Conv, x: torch.Tensor, out: torch.Tensor, T: int, H: int, W: int, res: Optional[torch.Tensor] = None,
+              stats: bool = False) -> Optional[torch.Tensor]:
+        """One implicit-GEMM convolution.  With `stats` the GroupNorm statistics of the OUTPUT come out of the convolution's epilogue
+        (s2v_conv_gemm_stats + s2v_vae_groupnorm_finalize): returns (mean, rstd) per group [G, 2] fp32 — the norm that consumes
+        `out` next does not read the volume again for them."""
         a = ConvArgs()
         a.x, a.ldx, a.w, a.ldw, a.bias = x.data_ptr(), x.shape[-1], cv.w.data_ptr(), cv.w.shape[1], cv.b.data_ptr()
         a.res, a.ldres = (res.data_ptr(), res.shape[-1]) if res is not None else (None, 0)
@@ -327,14 +336,26 @@ class VaeDecoderEngine:
             CONV_FLOPS["algorithmic"] = CONV_FLOPS.get("algorithmic", 0.0) + per_pos * T * H * W
             CONV_FLOPS["launched"] = CONV_FLOPS.get("launched", 0.0) + per_pos * T * (H + 2) * (W + 2)
             CONV_FLOPS["launches"] = CONV_FLOPS.get("launches", 0) + 1
-        _call("s2v_conv_gemm", C.byref(a), _stream())
+        if not stats:
+            _call("s2v_conv_gemm", C.byref(a), _stream())
+            return None
+        need = ((T * (H + 2) * (W + 2) + 127) // 128) * cv.cout * 2
+        if self._partial.numel() < need:
+            self._partial = torch.empty(need, device=self.device, dtype=torch.float32)
+        nblk = C.c_int32(0)
+        _call("s2v_conv_gemm_stats", C.byref(a), self._partial.data_ptr(), C.byref(nblk), _stream())
+        st = torch.empty(self.G * 2, device=self.device, dtype=torch.float32)
+        _call("s2v_vae_groupnorm_finalize", self._partial.data_ptr(), st.data_ptr(), nblk.value, T, H, W, cv.cout, self.G, 1e-6, _stream())
+        return st
 
     def _spatialnorm_silu(self, nm: _Norm, x: torch.Tensor, out: torch.Tensor, yb_all: torch.Tensor, T: int, H: int, W: int, Tl: int,
-                          hl: int, wl: int):
-        """yb_all [Tl*hl*wl, yb_cols]: conv_y | conv_b of every norm layer at latent resolution (decode_call)."""
-        stats = torch.empty(self.G * 2, device=self.device, dtype=torch.float32)
-        _call("s2v_vae_groupnorm_stats", x.data_ptr(), self._partial.data_ptr(), stats.data_ptr(), T, H, W, nm.C, self.G, GN_BLOCKS, 1e-6,
-              _stream())
+                          hl: int, wl: int, stats: Optional[torch.Tensor] = None):
+        """yb_all [Tl*hl*wl, yb_cols]: conv_y | conv_b of every norm layer at latent resolution (decode_call).  `stats` = the
+        (mean, rstd) table the producing convolution's epilogue left (FUSED_GN_STATS); without it the volume is read once more."""
+        if stats is None:
+            stats = torch.empty(self.G * 2, device=self.device, dtype=torch.float32)
+            _call("s2v_vae_groupnorm_stats", x.data_ptr(), self._partial.data_ptr(), stats.data_ptr(), T, H, W, nm.C, self.G, GN_BLOCKS, 1e-6,
+                  _stream())
         src = (C.c_int32 * T)(*spatialnorm_frame_src(T, Tl))
         _call("s2v_vae_spatialnorm_silu", x.data_ptr(), out.data_ptr(), stats.data_ptr(), nm.gamma.data_ptr(), nm.beta.data_ptr(),
               yb_all.data_ptr() + 2 * nm.yb_off, yb_all.shape[1], src, T, H, W, nm.C, self.G, hl, wl, _stream())
@@ -353,16 +374,17 @@ class VaeDecoderEngine:
         c.copy_(U[T:T + 2])
         new_cache[key] = c
 
-    def _resnet(self, name: str, x: torch.Tensor, xtag: str, zrows, T, H, W, Tl, hl, wl, cache, new_cache) -> Tuple[torch.Tensor, str]:
+    def _resnet(self, name: str, x: torch.Tensor, xtag: str, zrows, T, H, W, Tl, hl, wl, cache, new_cache,
+                xstats: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, str, Optional[torch.Tensor]]:
         r = self.res[name]
         cin, cout = r["norm1"].C, r["conv1"].cout
         u = self._vol("u", T, H, W, cin)
-        self._spatialnorm_silu(r["norm1"], x, u, zrows, T, H, W, Tl, hl, wl)
+        self._spatialnorm_silu(r["norm1"], x, u, zrows, T, H, W, Tl, hl, wl, stats=xstats)
         self._context(f"{name}.conv1", u, T, cache, new_cache)
         h = self._vol("h", T, H, W, cout)
-        self._conv(r["conv1"], u, h, T, H, W)
+        hstats = self._conv(r["conv1"], u, h, T, H, W, stats=FUSED_GN_STATS)
         u2 = self._vol("u", T, H, W, cout)
-        self._spatialnorm_silu(r["norm2"], h, u2, zrows, T, H, W, Tl, hl, wl)
+        self._spatialnorm_silu(r["norm2"], h, u2, zrows, T, H, W, Tl, hl, wl, stats=hstats)
         self._context(f"{name}.conv2", u2, T, cache, new_cache)
         res = x
         if r["short"] is not None:
@@ -370,8 +392,8 @@ class VaeDecoderEngine:
             self._conv(r["short"], x, res, T, H, W)
         otag = "x1" if xtag == "x0" else "x0"
         out = self._vol(otag, T, H, W, cout)
-        self._conv(r["conv2"], u2, out, T, H, W, res=res)
-        return out, otag
+        ostats = self._conv(r["conv2"], u2, out, T, H, W, res=res, stats=FUSED_GN_STATS)     # every resnet output feeds a norm next
+        return out, otag, ostats
 
     def decode_call(self, z: torch.Tensor, f0: int, Tl: int, i0: int, j0: int, hl: int, wl: int, scale: float,
                     cache: Dict[str, torch.Tensor], video: torch.Tensor, v0: int) -> Tuple[Dict[str, torch.Tensor], int]:
@@ -389,12 +411,12 @@ class VaeDecoderEngine:
         col = self._vol("col", T, H, W, 27 * Cz)
         _call("s2v_vae_latent_im2col", z.data_ptr(), col[2:].data_ptr(), Cz, Tz, hz, wz, f0, Tl, i0, j0, hl, wl, scale, _stream())
         x, tag = self._vol("x0", T, H, W, self.ch[0]), "x0"
-        self._conv(self.conv_in, col, x, T, H, W)
+        xst = self._conv(self.conv_in, col, x, T, H, W, stats=FUSED_GN_STATS)
         for i in range(2):
-            x, tag = self._resnet(f"mid_block.resnets.{i}", x, tag, zrows, T, H, W, Tl, hl, wl, cache, new_cache)
+            x, tag, xst = self._resnet(f"mid_block.resnets.{i}", x, tag, zrows, T, H, W, Tl, hl, wl, cache, new_cache, xst)
         for b in range(len(self.ch)):
             for i in range(self.layers + 1):
-                x, tag = self._resnet(f"up_blocks.{b}.resnets.{i}", x, tag, zrows, T, H, W, Tl, hl, wl, cache, new_cache)
+                x, tag, xst = self._resnet(f"up_blocks.{b}.resnets.{i}", x, tag, zrows, T, H, W, Tl, hl, wl, cache, new_cache, xst)
             if b != len(self.ch) - 1:
                 ct = b < self.t_levels
                 T2 = out_frames(T, ct)
@@ -404,9 +426,9 @@ class VaeDecoderEngine:
                 T, H, W = T2, 2 * H, 2 * W
                 tag = "x1" if tag == "x0" else "x0"
                 x = self._vol(tag, T, H, W, self.ch[b])
-                self._conv(self.ups[b], up, x, T, H, W)
+                xst = self._conv(self.ups[b], up, x, T, H, W, stats=FUSED_GN_STATS)
         u = self._vol("u", T, H, W, self.ch[-1])
-        self._spatialnorm_silu(self.norm_out, x, u, zrows, T, H, W, Tl, hl, wl)
+        self._spatialnorm_silu(self.norm_out, x, u, zrows, T, H, W, Tl, hl, wl, stats=xst)
         self._context("conv_out", u, T, cache, new_cache)
         o = self._vol("o", T, H, W, self.conv_out.cout)
         self._conv(self.conv_out, u, o, T, H, W)

@@ -199,6 +199,15 @@ typedef struct {
     int32_t T, t_pad, Hp, Wp, cin, cout, taps;
 } s2v_conv_args;
 S2V_API int s2v_conv_gemm(const s2v_conv_args* c, void* stream);
+/* The same convolution with the GroupNorm statistics of its OUTPUT fused into the epilogue: per row-block partial sums
+ * stats_partial[row_blocks, cout, 2] fp32 (sum, sum of squares of the bf16 values that are stored, over the T real frames; the zero
+ * border ring adds nothing) in a fixed order (deterministic); *row_blocks (host) receives the number of row blocks written
+ * (<= ceil(T*Hp*Wp / 128), which sizes the caller's buffer).  s2v_vae_groupnorm_finalize turns them into (mean, rstd) per group.
+ * Replaces the separate read of the volume by s2v_vae_groupnorm_stats when the normalised tensor is a convolution output — every
+ * nn.GroupNorm input of CogVideoXDecoder3D is (autoencoder_kl_cogvideox.py:297,306,974). */
+S2V_API int s2v_conv_gemm_stats(const s2v_conv_args* c, float* stats_partial, int32_t* row_blocks, void* stream);
+S2V_API int s2v_vae_groupnorm_finalize(const float* stats_partial, float* stats, int32_t row_blocks, int32_t T, int32_t H, int32_t W,
+                                       int32_t C, int32_t G, float eps, void* stream);
 
 /* Latent tile -> GEMM operands.  z is ONE sample [C, Tz, hz, wz] bf16; the tile is frames [f0, f0+T), rows [i0, i0+ht),
  * cols [j0, j0+wt); values are multiplied by `scale` (= 1/scaling_factor, pipeline_cogvideox.py:348) in fp32 and rounded.
