@@ -11,8 +11,9 @@ importlib.import_module("disentangled-subject-to-vid_b200").
     lora                         PEFT-layout LoRA adapters, read in place
     vae                          3D causal VAE decoder (implicit-GEMM convs) behind AutoencoderKLCogVideoX.decode
     parallel                     prompt / CFG sharding over the GPUs of one node (torch.distributed)
+    t5                           T5 v1.1 prompt encoder behind an attached transformers.T5EncoderModel
 """
-from . import _lib, engine, lora, modules, ops, parallel, pipeline, scheduler, tables, vae  # noqa: F401
+from . import _lib, engine, lora, modules, ops, parallel, pipeline, scheduler, t5, tables, vae  # noqa: F401
 from .lora import inject_lora, load_lora_state_dict  # noqa: F401
 from .modules import (  # noqa: F401
     Attention,
@@ -23,6 +24,7 @@ from .modules import (  # noqa: F401
 )
 from .pipeline import CogVideoXPipelineOutput, CustomCogVideoXPipeline, export_to_video, postprocess_video  # noqa: F401
 from .scheduler import CogVideoXDDIMScheduler, CogVideoXDPMScheduler  # noqa: F401
+from .t5 import attach_t5  # noqa: F401
 from .vae import AutoencoderKLCogVideoX, attach_vae, encode_reference_image  # noqa: F401
 
 __version__ = "0.1.0"

@@ -93,6 +93,10 @@ SIGNATURES = {
     "s2v_vae_groupnorm_silu": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "s2v_vae_subsample2": [_vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "s2v_video_to_uint8": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "s2v_gather_rows": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
+    "s2v_rmsnorm": [_vp, _vp, _vp, _i32, _i32, _f32, _vp],
+    "s2v_gated_gelu": [_vp, _vp, _i64, _i32, _vp],
+    "s2v_t5_attention": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "s2v_vae_blend": [_vp, _vp, _i64, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _vp],
 }
 

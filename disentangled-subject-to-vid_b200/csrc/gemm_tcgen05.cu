@@ -811,7 +811,10 @@ extern "C" int s2v_linear(const s2v_linear_args* a, void* stream_) {
     if (rc) return rc;
     // 256-wide tiles for the big projections, 128-wide when N is small or a LoRA group boundary is not 256-aligned
     const int gn = (a->lora_t && a->lora_group_n > 0) ? a->lora_group_n : a->N;
-    const bool wide = (a->N >= 256) && (gn % 256 == 0 || !a->lora_t || gn == a->N);
+    bool wide = (a->N >= 256) && (gn % 256 == 0 || !a->lora_t || gn == a->N);
+    // few rows (the T5 prompt encoder: 452): 256-wide tiles would leave SMs without a tile — the launch is weight-bandwidth
+    // bound, so more, narrower tiles stream the weights through more SMs
+    if (wide && (long long)((a->M + GEMM_BM - 1) / GEMM_BM) * ((a->N + 255) / 256) < sm_count()) wide = false;
     const bool two = wide && use_cta_pairs(a->M, a->N);
     switch (a->epilogue) {
         case S2V_EPI_BIAS:

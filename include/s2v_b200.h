@@ -282,6 +282,19 @@ S2V_API int s2v_outproj_lora_gate_residual(const s2v_linear_args* a, void* strea
 S2V_API int s2v_ffn_up_gelu_lora(const s2v_linear_args* a, void* stream);             /* K10 first half                       */
 S2V_API int s2v_ffn_down_lora_gate_residual(const s2v_linear_args* a, void* stream);  /* K10 second half + K8                 */
 
+/* ------------------------------------------------------------------------------------------------ T5 prompt encoder
+ * The pieces of transformers' modeling_t5.py around the projections (which go through s2v_linear), for the encoder call of
+ * D/pipelines/cogvideo/pipeline_cogvideox.py:197-237 (S/inference.py:185-189 loads T5EncoderModel): 226 tokens, no attention mask.
+ *   s2v_gather_rows   out[i,:] = table[ids[i],:]                          nn.Embedding (shared.weight); ids int64 on the device
+ *   s2v_rmsnorm       out = w * bf16(x * rsqrt(mean(x^2) + eps))          T5LayerNorm.forward (variance in fp32, both roundings)
+ *   s2v_gated_gelu    out[m,f] = bf16(gelu_new(g[m,f])) * g[m,F+f]        T5DenseGatedActDense with wi_0 | wi_1 stacked along N
+ *   s2v_t5_attention  softmax(bf16(q k^T) + bias) v per (batch, head), head_dim 64, NO 1/sqrt(d), bias [H,S,S] bf16 (the relative
+ *                     position table gathered by bucket), qkv [B,S,3*H*64] (q|k|v), out [B,S,H*64]; S <= 512     T5Attention.forward */
+S2V_API int s2v_gather_rows(const void* table, const int64_t* ids, void* out, int32_t n, int32_t D, int32_t V, void* stream);
+S2V_API int s2v_rmsnorm(const void* x, const void* w, void* out, int32_t rows, int32_t D, float eps, void* stream);
+S2V_API int s2v_gated_gelu(const void* g, void* out, int64_t M, int32_t F, void* stream);
+S2V_API int s2v_t5_attention(const void* qkv, const void* bias, void* out, int32_t B, int32_t S, int32_t H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

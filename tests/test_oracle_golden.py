@@ -174,3 +174,23 @@ def test_dpm_step_trace_bit_exact(golden_dir, tag, snr):
         assert np.array_equal(prev.numpy(), g[f"dpm_{tag}_prev"][i]), (tag, i)
         assert np.array_equal(old.numpy(), g[f"dpm_{tag}_x0"][i]), (tag, i)
         sample = prev.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------ T5 prompt encoder oracle vs transformers' own output
+def test_t5_oracle_reproduces_transformers_golden(golden_dir):
+    """oracle/t5_oracle.py against tests/golden/t5_tiny.pt (transformers 5.5.0 T5EncoderModel, gated-gelu, 226 padded tokens, no
+    mask): fp32 to rounding noise, and the bf16 execution bit for bit (same torch ops in the same order)."""
+    from oracle import t5_oracle as T
+    fx = torch.load(os.path.join(golden_dir, "t5_tiny.pt"))
+    c = fx["cfg"]
+    cfg = T.T5Config(d_model=c["d_model"], d_kv=c["d_kv"], d_ff=c["d_ff"], num_layers=c["num_layers"], num_heads=c["num_heads"],
+                     vocab_size=c["vocab_size"])
+    out = T.encoder_forward(fx["state"], cfg, fx["ids"])
+    assert float((out - fx["out_fp32"]).abs().max()) <= 1e-5
+    p16 = {k: v.to(torch.bfloat16) for k, v in fx["state"].items()}
+    assert torch.equal(T.encoder_forward(p16, cfg, fx["ids"]).float(), fx["out_bf16"])
+    # the relative-position bucket table is integer arithmetic: product copy == oracle == a few known values
+    from s2v_b200 import t5
+    rel = torch.arange(-300, 301)
+    assert torch.equal(t5.relative_position_bucket(rel), T.relative_position_bucket(rel))
+    assert T.relative_position_bucket(torch.tensor([0, 1, -1, 7, 8, -8, 127, 128, -500])).tolist() == [0, 17, 1, 23, 24, 8, 31, 31, 15]
