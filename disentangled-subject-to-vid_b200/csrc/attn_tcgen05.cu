@@ -42,6 +42,8 @@
 //
 // Global layout: qkv [B, S, 3*H*64] (q|k|v, heads contiguous) read through ONE 4-D tensor map {64, 3H, S, B};
 // out [B, S, H*64].  Key rows >= S are zero-filled by TMA and masked to -inf; query rows >= S are not stored.
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_util.h"
 #include "s2v_b200.h"
@@ -58,7 +60,7 @@ constexpr int ATT_POLY16_DEFAULT = 1;  // of every 8 PAIRS (16 exponentials), ho
 // (2 x 32 + 4 x 80 + 2 x 64 = 512 columns): 10 % fewer tcgen05.mma per key for the single issuing thread and 20 % fewer barrier
 // round trips per key for the softmax warps
 __host__ __device__ constexpr uint32_t att_tile_bytes(int bk) { return uint32_t(bk) * ATT_D * 2; }   // 8 / 10 KB
-__host__ __device__ constexpr uint32_t att_smem_bytes(int bk) { return 2 * ATT_STAGES * att_tile_bytes(bk) + 1024 + 256; }
+__host__ __device__ constexpr uint32_t att_smem_bytes(int bk) { return 2 * ATT_STAGES * att_tile_bytes(bk) + 1024 + 512; }
 constexpr float ATT_P_LIMIT_LOG2 = 64.0f;     // probabilities are kept below 2^64 relative to the reference max
 constexpr float ATT_SUM_LIMIT = 1.8446744e19f;  // 2^64
 
@@ -109,14 +111,79 @@ __device__ __forceinline__ void exp2_poly2(uint64_t X, float& r0, float& r1, flo
     r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-template <int BK, int POLY16, bool HI, bool MC>
+// MODE bits (template parameter; 0 = the round-1/2 schedule):
+//   ATT_POOL  the score buffers are ONE pool of 5 (Q 64 | 5 x 64 | O 128 columns) handed out in the fixed order q0 t0, q1 t0, q0 t1, ...
+//             (score product number k = 2 t + q lives in buffer k % 5): S_q(t) is issued as soon as the PV product that last used
+//             its buffer (number k - 5) has been issued, i.e. about TWO tiles ahead of the softmax instead of one, with P still
+//             stored over its own scores (no extra barrier);
+//   ATT_PIPE  software-pipelined softmax: the tile is processed in two 32-key halves, the second half's tcgen05.ld runs under the
+//             first half's exponentials, the NEXT tile's first half is fetched under the second half's, and the p_ready arrive of
+//             tile t (tcgen05.wait::st + fence + arrive) is issued after the first half of tile t + 1 — no TMEM round trip is
+//             left on the warp's critical path when the scores are early (which ATT_POOL makes the normal case);
+//   ATT_DEFER (without ATT_PIPE) only the arrive is deferred: after the next tile's loads have been issued.
+//   ATT_LATE  (with ATT_PIPE) the next tile's first half is requested at the END of the tile, right after P has been stored, and P is
+//             published there (no deferral): keeps the whole score look-ahead for the issuing thread.
+//   ATT_TRACE (measurement only, classic loop) CTA (1, 0, 0) records %clock at the phase boundaries of tiles 64..79 of every softmax warp and
+//             of the issuing thread's PV / S issues into dbg + ATT_TRACE_OFF (tools/attn_trace.py prints the timeline).
+//   ATT_GUARD phase guard between the two softmax warps of a sub-partition (query tiles 0 and 1 of the same lane quarter): left alone they
+//             drift into lock-step — both in their exponentials (sharing the XU at half rate each), then both in their load / store /
+//             barrier phase with the XU idle (profiles/r02b_attn_trace.txt).  With the guard warp q1 starts the exponentials of tile t
+//             only when its partner has issued the first GUARD_AT of tile t's, and q0 starts tile t + 1 only when q1 is that far into
+//             tile t: the two alternate, one warp's non-exponential phase always lies under the other's exponentials.
+constexpr int ATT_POOL = 1, ATT_PIPE = 2, ATT_DEFER = 4, ATT_LATE = 8, ATT_TRACE = 16, ATT_GUARD = 32;
+constexpr int ATT_TRACE_T0 = 64, ATT_TRACE_NT = 16, ATT_TRACE_STAMPS = 6;
+constexpr unsigned long long ATT_TRACE_OFF = 2 + 3ull * 76 * 48 * 2;    // behind the per-CTA records of the cfg-3 grid
+__device__ __forceinline__ uint32_t clock32() {
+    uint32_t c;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+    return c;
+}
+constexpr int ATT_NPOOL = 5;
+
+// score-buffer sequence of one query-tile chain: (buffer index, mbarrier phase parity) of tile t, advanced tile by tile
+template <bool POOL>
+struct AttBufIter {
+    int j;
+    uint32_t par;
+    __device__ __forceinline__ explicit AttBufIter(int q) : j(POOL ? q : 2 * q), par(0) {}
+    __device__ __forceinline__ void next() {
+        if constexpr (POOL) {
+            j += 2;
+            if (j >= ATT_NPOOL) { j -= ATT_NPOOL; par ^= 1u; }
+        } else {
+            j ^= 1;
+            if ((j & 1) == 0) par ^= 1u;
+        }
+    }
+};
+
+// tcgen05.wait::ld that also "produces" the loaded registers, so that no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+template <int BK, int POLY16, bool HI, bool MC, int MODE = 0, int GUARD_AT = 32>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H,
                 float scale_log2, int skew_ns, unsigned long long* __restrict__ dbg) {
     constexpr int W_TMA = HI ? 8 : 0, W_MMA = HI ? 9 : 1, W_SOFT0 = HI ? 0 : 4;   // warp roles (see the header comment)
     constexpr int ATT_BK = BK;
     constexpr uint32_t ATT_TILE_BYTES = att_tile_bytes(BK);
-    static_assert(BK % 16 == 0 && TM_S + 4 * BK <= TM_O, "score buffers must fit between Q and O");
+    constexpr bool POOL = (MODE & ATT_POOL) != 0, PIPE = (MODE & ATT_PIPE) != 0, DEFER = (MODE & ATT_DEFER) != 0;
+    constexpr bool LATE = (MODE & ATT_LATE) != 0;
+    constexpr bool TRACE = (MODE & ATT_TRACE) != 0;
+    constexpr bool GUARD = (MODE & ATT_GUARD) != 0;
+    static_assert(!GUARD || (BK == 64 && !PIPE && GUARD_AT % 16 == 0 && GUARD_AT > 0 && GUARD_AT < 64), "guard: classic loop, 64-key tiles");
+    const bool tracing = TRACE && dbg && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0;
+    constexpr int NBUF = POOL ? ATT_NPOOL : 4;     // score buffers (and s_full / p_ready barriers)
+    static_assert(BK % 16 == 0 && TM_S + NBUF * BK <= TM_O, "score buffers must fit between Q and O");
+    static_assert(!PIPE || BK == 64, "the pipelined softmax is written for 64-key tiles");
     extern __shared__ uint8_t smem_raw[];
     unsigned long long dbg_c0 = 0, dbg_t0 = 0;
     if (dbg && threadIdx.x == 0) {
@@ -129,12 +196,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_STAGES * ATT_TILE_BYTES);
     uint64_t* kv_full = bars;                     // STAGES
     uint64_t* kv_empty = kv_full + ATT_STAGES;    // STAGES
-    uint64_t* s_full = kv_empty + ATT_STAGES;     // 4: [q][buf]
-    uint64_t* p_ready = s_full + 4;               // 4: [q][tile parity]
-    uint64_t* p_free = p_ready + 4;               // 2
+    uint64_t* s_full = kv_empty + ATT_STAGES;     // 4: [q][buf]            (ATT_POOL: 5, one per pool buffer)
+    uint64_t* p_ready = s_full + ATT_NPOOL;       // 4: [q][tile parity]    (ATT_POOL: 5)
+    uint64_t* p_free = p_ready + ATT_NPOOL;       // 2
     uint64_t* q_ready = p_free + 2;               // 1
     uint64_t* o_final = q_ready + 1;              // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
+    volatile uint32_t* prog = tmem_slot + 2;       // ATT_GUARD: [q][lane quarter] progress marks (2 t + 1 = GUARD_AT exponentials of tile t issued)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -152,14 +220,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], MC ? 2 : 1);     // MC: one tcgen05.commit arrive from each CTA of the pair
         }
-        for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+        for (int i = 0; i < NBUF; ++i) mbar_init(&s_full[i], 1);
         // p_ready is double buffered by tile parity: without a per-tile p_free wait a fast softmax warp may finish tile t+1
         // before a slow one has arrived for tile t (it cannot get further: S(t+2) is only issued after p_ready(t)), and
         // two arrivals of one warp must never land in the same barrier phase.
-        for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], 4);  // one arrive per softmax warp of the query tile
+        for (int i = 0; i < NBUF; ++i) mbar_init(&p_ready[i], 4);  // one arrive per softmax warp of the query tile
         for (int q = 0; q < 2; ++q) mbar_init(&p_free[q], 1);
         mbar_init(q_ready, 8);
         mbar_init(o_final, 1);
+        for (int i = 0; i < 8; ++i) prog[i] = 0u;
         fence_barrier_init();
     }
     __syncwarp();
@@ -199,21 +268,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
             // ---------------------------------------------------------------- MMA issuer
             constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BK, 0, 0);   // S = Q K^T   (A in TMEM, B K-major)
             constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_D, 0, 1);    // O += P V    (A in TMEM, B MN-major)
-            auto issue_s = [&](int q, int stage, int buf) {
+            auto issue_s_buf = [&](int q, int stage, int j) {     // j = score buffer index
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + stage * ATT_TILE_BYTES), 16, 1024);
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)
-                    umma_ts(tmem_base + TM_S + (q * 2 + buf) * BK, tmem_base + TM_Q + q * 32 + k * 8, bdesc + uint64_t(k * 2),
-                            idesc_s, k != 0);
+                    umma_ts(tmem_base + TM_S + j * BK, tmem_base + TM_Q + q * 32 + k * 8, bdesc + uint64_t(k * 2), idesc_s, k != 0);
             };
-            auto issue_pv = [&](int q, int stage, bool accumulate, int t) {
+            auto issue_pv_buf = [&](int q, int stage, bool accumulate, int j) {
                 // V tile [BK keys][64 d]: 16 keys per MMA = two 8-row groups = 2048 bytes
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + stage * ATT_TILE_BYTES), 1024, 1024);
 #pragma unroll
                 for (int k = 0; k < ATT_BK / 16; ++k)
-                    umma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_S + (q * 2 + (t & 1)) * BK + k * 8, bdesc + uint64_t(k * 128), idesc_o,
+                    umma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_S + j * BK + k * 8, bdesc + uint64_t(k * 128), idesc_o,
                             (accumulate || k != 0) ? 1u : 0u);
             };
+            auto issue_s = [&](int q, int stage, int buf) { issue_s_buf(q, stage, q * 2 + buf); };
+            auto issue_pv = [&](int q, int stage, bool accumulate, int t) { issue_pv_buf(q, stage, accumulate, q * 2 + (t & 1)); };
             auto release_kv = [&](int stage) {
                 if (MC) umma_commit_mcast(&kv_empty[stage], 3); else umma_commit(&kv_empty[stage]);
             };
@@ -237,6 +307,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                         need_kv(t);
                         release_kv(t % ATT_STAGES);
                     }
+                } else if constexpr (POOL) {
+                    // ---- pool schedule: score product k = 2 t + q goes to buffer k % 5, in strictly increasing k, as soon as PV
+                    // number k - 5 (the previous tenant of that buffer) has been issued; PV_q(t) is issued when P_q(t) is ready.
+                    // K/V ring: S number k needs tile k >> 1 <= (oldest unissued PV's tile) + 3 < + ATT_STAGES, so a blocking
+                    // need_kv never waits for a stage that only this thread could release (same bound with the partner CTA).
+                    mbar_wait(q_ready, 0);
+                    tc_fence_after();
+                    const int total = 2 * n_kv;
+                    int s_next = 0, sj = 0;         // next score product and its buffer (s_next % 5)
+                    int tq0 = 0, tq1 = 0;           // PV products issued per chain        (scalars: indexed arrays went to local memory)
+                    int pj0 = 0, pj1 = 1;           // buffer of chain q's next PV ((2 tq_q + q) % 5)
+                    uint32_t pp0 = 0, pp1 = 0;      // and its p_ready phase parity
+                    auto serve = [&](int q, int& tq, int tq_other, int& pj, uint32_t& pp) {
+                        const int t = tq;
+                        if (t < n_kv && 2 * t + q < s_next && mbar_test_wait(&p_ready[pj], pp)) {
+                            tc_fence_after();
+                            issue_pv_buf(q, t % ATT_STAGES, t != 0, pj);
+                            umma_commit(&p_free[q]);
+                            tq = t + 1;
+                            pj += 2;
+                            if (pj >= ATT_NPOOL) { pj -= ATT_NPOOL; pp ^= 1u; }
+                            if (tq_other > t) release_kv(t % ATT_STAGES);   // both PV(t) issued: K(t)/V(t) may be refilled
+                        }
+                    };
+                    while (tq0 < n_kv || tq1 < n_kv) {
+                        while (s_next < total) {
+                            const int kp = s_next - ATT_NPOOL;          // previous tenant of the buffer
+                            if (kp >= 0 && ((kp & 1) ? tq1 : tq0) <= (kp >> 1)) break;
+                            need_kv(s_next >> 1);
+                            issue_s_buf(s_next & 1, (s_next >> 1) % ATT_STAGES, sj);
+                            umma_commit(&s_full[sj]);
+                            ++s_next;
+                            if (++sj == ATT_NPOOL) sj = 0;
+                        }
+                        serve(0, tq0, tq1, pj0, pp0);
+                        serve(1, tq1, tq0, pj1, pp1);
+                    }
+                    umma_commit(o_final);
                 } else {
                 mbar_wait(q_ready, 0);
                 tc_fence_after();
@@ -259,6 +367,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                         // two issuers can only block on each other if each is more than 2 tiles ahead of the other — impossible.
                         if (t < n_kv && t < tq[q ^ 1] + 4 && mbar_test_wait(&p_ready[q * 2 + (t & 1)], (t >> 1) & 1)) {
                             tc_fence_after();
+                            if (TRACE && tracing && t >= ATT_TRACE_T0 && t < ATT_TRACE_T0 + ATT_TRACE_NT)
+                                dbg[ATT_TRACE_OFF + 8 * ATT_TRACE_NT * ATT_TRACE_STAMPS + (q * ATT_TRACE_NT + (t - ATT_TRACE_T0)) * 2] = clock32();
                             issue_pv(q, t % ATT_STAGES, t != 0, t);
                             umma_commit(&p_free[q]);
                             if (t + 2 < n_kv) {
@@ -266,6 +376,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                                 issue_s(q, (t + 2) % ATT_STAGES, t & 1);
                                 umma_commit(&s_full[q * 2 + (t & 1)]);
                             }
+                            if (TRACE && tracing && t >= ATT_TRACE_T0 && t < ATT_TRACE_T0 + ATT_TRACE_NT)
+                                dbg[ATT_TRACE_OFF + 8 * ATT_TRACE_NT * ATT_TRACE_STAMPS + (q * ATT_TRACE_NT + (t - ATT_TRACE_T0)) * 2 + 1] = clock32();
                             tq[q] = t + 1;
                             if (tq[q ^ 1] > t) release_kv(t % ATT_STAGES);   // both PV(t) issued: K(t)/V(t) may be refilled
                         }
@@ -282,7 +394,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
         const int q = (warp - W_SOFT0) >> 2;    // query tile of this warpgroup
         const int lq = warp & 3;                // TMEM lane quarter
         const uint32_t lane_off = uint32_t(lq * 32) << 16;
-        const uint32_t tSb = tmem_base + lane_off + TM_S + q * 2 * BK;
         const uint32_t tO = tmem_base + lane_off + TM_O + q * 64;
         const int row = q_row0 + q * ATT_BQ + lq * 32 + lane;
 
@@ -316,23 +427,97 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
         float mneg = 0.f;          // -m_ref * scale_log2
         float l_sum = 0.f;
         const uint64_t C2 = pack2(scale_log2, scale_log2);
+        const uint32_t tS0 = tmem_base + lane_off + TM_S;      // score buffer j of this lane quarter at tS0 + j * BK
 
-        for (int t = 0; t < n_kv; ++t) {
-            const int buf = t & 1;
-            mbar_wait(&s_full[q * 2 + buf], (t >> 1) & 1);
+        // ---- exact-max path (tile 0, or a probability would leave the 2^64 window): move the reference, rescale O and l,
+        // recompute the tile's probabilities from its raw scores.  `s` holds the tile's BK raw scores (masked).
+        auto exact_tile = [&](const uint32_t (&s)[BK], uint32_t (&pk)[BK / 2], int t) -> float {
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < BK; i += 4) {
+                mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+                mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+            }
+            const float m_new = fmaxf(m_ref, fmaxf(mx0, mx1));
+            if (t != 0) {
+                const float factor = ex2_approx((m_ref - m_new) * scale_log2);   // 1 when the reference does not move
+                l_sum *= factor;
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+                    uint32_t o[32];
+                    tmem_ld32(tO + cb * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                    tmem_st32(tO + cb * 32, o);
+                }
+                tmem_st_wait();
+            }
+            m_ref = m_new;
+            mneg = -m_new * scale_log2;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < BK; i += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, mneg));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg));
+                a0 += p0;
+                a1 += p1;
+                pk[i / 2] = pack_bf16x2(p0, p1);
+            }
+            return a0 + a1;
+        };
+        // ---- fast path over N consecutive scores (N % 16 == 0): exponentials against the standing reference max
+        auto fast_part = [&](auto& s, auto& pk, auto n_tag, uint64_t M2, uint64_t& acc0, uint64_t& acc1, float& xmax) {
+            constexpr int N = decltype(n_tag)::value;
+#pragma unroll
+            for (int i = 0; i < N; i += 8) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const uint64_t X = ffma2(pack2(__uint_as_float(s[i + 2 * h]), __uint_as_float(s[i + 2 * h + 1])), C2, M2);
+                    float p0, p1;
+                    if (((i >> 3) & 1) * 4 + h < POLY16) {
+                        exp2_poly2(X, p0, p1, xmax);
+                    } else {
+                        float x0, x1;
+                        unpack2(X, x0, x1);
+                        p0 = ex2_approx(x0);
+                        p1 = ex2_approx(x1);
+                    }
+                    if (h & 1) acc1 = fadd2(acc1, pack2(p0, p1)); else acc0 = fadd2(acc0, pack2(p0, p1));
+                    pk[i / 2 + h] = pack_bf16x2(p0, p1);
+                }
+            }
+        };
+        auto publish = [&](int j) {     // P stored into buffer j is complete: hand it to the issuing thread
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[j]);
+        };
+
+        if constexpr (!PIPE) {
+        AttBufIter<POOL> it(q);
+        int j_prev = 0;
+        for (int t = 0; t < n_kv; ++t, it.next()) {
+            uint32_t st0 = 0, st1 = 0, st2 = 0, st3 = 0, st4 = 0;
+            if (TRACE) st0 = clock32();
+            mbar_wait(&s_full[it.j], it.par);
             tc_fence_after();
+            if (TRACE) st1 = clock32();
             uint32_t s[BK];
             {
                 uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
                 uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-                tmem_ld32(tSb + buf * BK, s0);
-                tmem_ld32(tSb + buf * BK + 32, s1);
+                tmem_ld32(tS0 + it.j * BK, s0);
+                tmem_ld32(tS0 + it.j * BK + 32, s1);
                 if constexpr (BK == 80) {
                     uint32_t(&s2)[16] = *reinterpret_cast<uint32_t(*)[16]>(&s[64]);
-                    tmem_ld16(tSb + buf * BK + 64, s2);
+                    tmem_ld16(tS0 + it.j * BK + 64, s2);
                 }
+                if (DEFER && t != 0) publish(j_prev);    // P(t-1): its store has had the barrier wait and the load issue to complete
                 tmem_ld_wait();
             }
+            if (TRACE) st2 = clock32();
             const int valid = S - t * ATT_BK;  // keys valid in this tile (>= BK except for the last tile)
             if (valid < ATT_BK) {
 #pragma unroll
@@ -342,28 +527,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
             uint32_t pk[BK / 2];
             float tsum;
             bool redo = (t == 0);
+            if (GUARD && (t != 0 || q == 1)) {   // wait for the partner warp's mark (see ATT_GUARD)
+                const uint32_t need = q == 1 ? 2u * t + 1u : 2u * (t - 1) + 1u;
+                while (prog[(q ^ 1) * 4 + lq] < need) {
+                }
+            }
             if (!redo) {
-                // ---- fast path: exponentials against the standing reference max
-                const uint64_t M2 = pack2(mneg, mneg);
                 uint64_t acc0 = 0ull, acc1 = 0ull;
                 float xmax = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < BK; i += 8) {
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const uint64_t X = ffma2(pack2(__uint_as_float(s[i + 2 * h]), __uint_as_float(s[i + 2 * h + 1])), C2, M2);
-                        float p0, p1;
-                        if (((i >> 3) & 1) * 4 + h < POLY16) {
-                            exp2_poly2(X, p0, p1, xmax);
-                        } else {
-                            float x0, x1;
-                            unpack2(X, x0, x1);
-                            p0 = ex2_approx(x0);
-                            p1 = ex2_approx(x1);
-                        }
-                        if (h & 1) acc1 = fadd2(acc1, pack2(p0, p1)); else acc0 = fadd2(acc0, pack2(p0, p1));
-                        pk[i / 2 + h] = pack_bf16x2(p0, p1);
-                    }
+                if constexpr (GUARD) {
+                    uint32_t(&sa)[GUARD_AT] = *reinterpret_cast<uint32_t(*)[GUARD_AT]>(&s[0]);
+                    uint32_t(&sb)[BK - GUARD_AT] = *reinterpret_cast<uint32_t(*)[BK - GUARD_AT]>(&s[GUARD_AT]);
+                    uint32_t(&pa)[GUARD_AT / 2] = *reinterpret_cast<uint32_t(*)[GUARD_AT / 2]>(&pk[0]);
+                    uint32_t(&pb)[(BK - GUARD_AT) / 2] = *reinterpret_cast<uint32_t(*)[(BK - GUARD_AT) / 2]>(&pk[GUARD_AT / 2]);
+                    fast_part(sa, pa, std::integral_constant<int, GUARD_AT>{}, pack2(mneg, mneg), acc0, acc1, xmax);
+                    asm volatile("" :: "r"(pa[GUARD_AT / 2 - 1]) : "memory");     // the mark is not hoisted above the first part's exponentials
+                    if (lane == 0) prog[q * 4 + lq] = 2u * t + 1u;
+                    fast_part(sb, pb, std::integral_constant<int, BK - GUARD_AT>{}, pack2(mneg, mneg), acc0, acc1, xmax);
+                } else {
+                    fast_part(s, pk, std::integral_constant<int, BK>{}, pack2(mneg, mneg), acc0, acc1, xmax);
                 }
                 float a, b, c, d;
                 unpack2(acc0, a, b);
@@ -372,63 +554,133 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 const bool bad = !(tsum < ATT_SUM_LIMIT) || (xmax > ATT_P_LIMIT_LOG2);
                 redo = __any_sync(0xffffffffu, bad);
             }
-            // P(t) is stored over the first BK/2 columns of its own score buffer S[q][t&1] (dead once it is in registers).  That
-            // buffer's previous tenant P(t-2) was consumed before S(t) could be written (the tensor pipe executes in order),
+            // P(t) is stored over the first BK/2 columns of its own score buffer (dead once it is in registers).  That
+            // buffer's previous tenant was consumed before S(t) could be written (the tensor pipe executes in order),
             // so the store needs no barrier wait; only the rare O rescale must know that PV_q(t-1) has finished.
             if (t != 0 && redo) {
                 mbar_wait(&p_free[q], (t - 1) & 1);
                 tc_fence_after();
             }
             if (redo) {
-                // ---- exact-max path (tile 0, or a probability would leave the 2^64 window): move the reference
-                float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < BK; i += 4) {
-                    mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-                    mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-                }
-                const float m_new = fmaxf(m_ref, fmaxf(mx0, mx1));
-                if (t != 0) {
-                    const float factor = ex2_approx((m_ref - m_new) * scale_log2);   // 1 when the reference does not move
-                    l_sum *= factor;
-#pragma unroll
-                    for (int cb = 0; cb < 2; ++cb) {
-                        uint32_t o[32];
-                        tmem_ld32(tO + cb * 32, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-                        tmem_st32(tO + cb * 32, o);
-                    }
-                    tmem_st_wait();
-                }
-                m_ref = m_new;
-                mneg = -m_new * scale_log2;
-                float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                for (int i = 0; i < BK; i += 2) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, mneg));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg));
-                    a0 += p0;
-                    a1 += p1;
-                    pk[i / 2] = pack_bf16x2(p0, p1);
-                }
-                tsum = a0 + a1;
+                tsum = exact_tile(s, pk, t);
+                if (GUARD && lane == 0) prog[q * 4 + lq] = 2u * t + 1u;      // (tile 0, or the mark was already set: idempotent)
             }
             l_sum += tsum;
+            if (TRACE) {
+                asm volatile("" :: "r"(pk[0]), "r"(pk[31]), "f"(tsum));
+                st3 = clock32();
+            }
             {
                 const uint32_t(&p0)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]);
-                tmem_st32(tSb + buf * BK, p0);
+                tmem_st32(tS0 + it.j * BK, p0);
                 if constexpr (BK == 80) {
                     const uint32_t(&p1)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&pk[32]);
-                    tmem_st8(tSb + buf * BK + 32, p1);
+                    tmem_st8(tS0 + it.j * BK + 32, p1);
                 }
             }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_ready[q * 2 + buf]);
+            if (TRACE) {
+                tmem_st_wait();
+                st4 = clock32();
+            }
+            if (DEFER) j_prev = it.j; else publish(it.j);
+            if (TRACE && tracing && lane == 0 && t >= ATT_TRACE_T0 && t < ATT_TRACE_T0 + ATT_TRACE_NT) {
+                unsigned long long* r = dbg + ATT_TRACE_OFF + ((warp - W_SOFT0) * ATT_TRACE_NT + (t - ATT_TRACE_T0)) * ATT_TRACE_STAMPS;
+                r[0] = st0; r[1] = st1; r[2] = st2; r[3] = st3; r[4] = st4; r[5] = clock32();
+            }
         }
+        if (DEFER) publish(j_prev);
+        } else {
+        // ---- software-pipelined form (ATT_PIPE; BK == 64): see the MODE comment above the kernel
+        AttBufIter<POOL> cur(q), nxt(q);
+        nxt.next();
+        uint32_t sA[32], sB[32];
+        uint32_t pk[32];
+        auto load_full_and_mask = [&](uint32_t (&s)[64], int j, int t) {
+            uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+            uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+            tmem_ld32(tS0 + j * BK, s0);
+            tmem_ld32(tS0 + j * BK + 32, s1);
+            tmem_ld_wait();
+            const int valid = S - t * ATT_BK;
+            if (valid < ATT_BK) {
+#pragma unroll
+                for (int i = 0; i < BK; ++i)
+                    if (i >= valid) s[i] = __float_as_uint(-INFINITY);
+            }
+        };
+        // tile 0: exact path, then the first half of tile 1 is requested before P(0) is published
+        mbar_wait(&s_full[cur.j], cur.par);
+        tc_fence_after();
+        {
+            uint32_t s[64];
+            load_full_and_mask(s, cur.j, 0);
+            l_sum += exact_tile(s, pk, 0);
+            tmem_st32(tS0 + cur.j * BK, pk);
+        }
+        if (n_kv > 1) {
+            mbar_wait(&s_full[nxt.j], nxt.par);
+            tc_fence_after();
+            tmem_ld32(tS0 + nxt.j * BK, sA);
+        }
+        int j_prev = cur.j;
+        if (LATE) publish(j_prev);
+        for (int t = 1; t < n_kv; ++t) {
+            cur = nxt;
+            nxt.next();
+            tmem_ld_wait_dep(sA);                                 // first half of S(t): requested half a tile ago
+            tmem_ld32(tS0 + cur.j * BK + 32, sB);                  // second half: arrives under the first half's exponentials
+            const int valid = S - t * ATT_BK;
+            if (valid < 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i >= valid) sA[i] = __float_as_uint(-INFINITY);
+            }
+            const uint64_t M2 = pack2(mneg, mneg);
+            uint64_t acc0 = 0ull, acc1 = 0ull;
+            float xmax = -INFINITY;
+            uint32_t(&pk0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[0]);
+            uint32_t(&pk1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[16]);
+            fast_part(sA, pk0, std::integral_constant<int, 32>{}, M2, acc0, acc1, xmax);
+            if (!LATE) publish(j_prev);                            // P(t-1): stored half a tile ago
+            tmem_ld_wait_dep(sB);
+            if (!LATE && t + 1 < n_kv) {                           // first half of S(t+1): early under ATT_POOL (issued two tiles ahead)
+                mbar_wait(&s_full[nxt.j], nxt.par);
+                tc_fence_after();
+                tmem_ld32(tS0 + nxt.j * BK, sA);
+            }
+            if (valid < 64) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i + 32 >= valid) sB[i] = __float_as_uint(-INFINITY);
+            }
+            fast_part(sB, pk1, std::integral_constant<int, 32>{}, M2, acc0, acc1, xmax);
+            float a, b, c, d;
+            unpack2(acc0, a, b);
+            unpack2(acc1, c, d);
+            float tsum = (a + b) + (c + d);
+            const bool bad = !(tsum < ATT_SUM_LIMIT) || (xmax > ATT_P_LIMIT_LOG2);
+            if (__any_sync(0xffffffffu, bad)) {
+                mbar_wait(&p_free[q], (t - 1) & 1);                // PV_q(t-1) has finished: O may be rescaled
+                tc_fence_after();
+                uint32_t s[64];
+                load_full_and_mask(s, cur.j, t);                   // (also completes the prefetch of S(t+1) into sA)
+                tsum = exact_tile(s, pk, t);
+            }
+            l_sum += tsum;
+            tmem_st32(tS0 + cur.j * BK, pk);
+            j_prev = cur.j;
+            if (LATE) {
+                if (t + 1 < n_kv) {
+                    mbar_wait(&s_full[nxt.j], nxt.par);
+                    tc_fence_after();
+                    tmem_ld32(tS0 + nxt.j * BK, sA);
+                }
+                publish(j_prev);
+            }
+        }
+        if (!LATE) publish(j_prev);
+        }
+
         // ---- epilogue: O / l -> bf16 -> global
         mbar_wait(o_final, 0);
         tc_fence_after();
@@ -548,6 +800,21 @@ extern "C" int s2v_attn_fwd(const void* qkv, void* o, int32_t B, int32_t S, int3
 extern "C" __attribute__((visibility("default"))) int s2v_attn_fwd_exp(const void* qkv, void* o, int32_t B, int32_t S, int32_t H,
                                                                        float softmax_scale, int32_t variant, int32_t poly16,
                                                                        int32_t skew_ns, void* dbg_u64x2, void* stream_) {
+    if (variant >= 16) {   // bits 4.. = MODE + 1 of the schedule experiments (64-key tiles, HI + MC, 1 polynomial pair in 8)
+        static const attn_kern_t modes[] = {
+            attn_fwd_kernel<64, 1, true, true, 0>, attn_fwd_kernel<64, 1, true, true, ATT_POOL>, attn_fwd_kernel<64, 1, true, true, ATT_DEFER>,
+            attn_fwd_kernel<64, 1, true, true, ATT_POOL | ATT_DEFER>, attn_fwd_kernel<64, 1, true, true, ATT_PIPE | ATT_LATE>,
+            attn_fwd_kernel<64, 1, true, true, ATT_POOL | ATT_PIPE | ATT_LATE>, attn_fwd_kernel<64, 1, true, true, ATT_POOL | ATT_PIPE>,
+            attn_fwd_kernel<64, 1, true, true, ATT_PIPE>, attn_fwd_kernel<64, 1, true, true, ATT_TRACE>,
+            attn_fwd_kernel<64, 1, true, true, ATT_GUARD, 32>, attn_fwd_kernel<64, 1, true, true, ATT_GUARD, 16>,
+            attn_fwd_kernel<64, 1, true, true, ATT_GUARD, 48>, attn_fwd_kernel<64, 1, true, true, ATT_GUARD | ATT_TRACE, 32>,
+            attn_fwd_kernel<64, 1, true, true, ATT_GUARD | ATT_DEFER, 32>};
+        const int m = (variant >> 4) - 1;
+        if (m < 0 || m >= int(sizeof(modes) / sizeof(modes[0])) || skew_ns < 0 || skew_ns > 100000)
+            return set_error(S2V_E_BADARG, "s2v_attn_fwd_exp: schedule experiment 0..13");
+        return launch_attn(modes[m], 64, true, qkv, o, B, S, H, softmax_scale, skew_ns, static_cast<unsigned long long*>(dbg_u64x2),
+                           static_cast<cudaStream_t>(stream_), "attn_fwd_kernel(mode)");
+    }
 #define S2V_ROW(P) {attn_fwd_kernel<64, P, false, false>, attn_fwd_kernel<64, P, true, false>, attn_fwd_kernel<64, P, false, true>, \
                     attn_fwd_kernel<64, P, true, true>, attn_fwd_kernel<80, P, false, false>, attn_fwd_kernel<80, P, true, false>, \
                     attn_fwd_kernel<80, P, false, true>, attn_fwd_kernel<80, P, true, true>}

@@ -13,6 +13,7 @@ prompt the 4.7 B-parameter T5-XXL is weight-bandwidth bound (9.4 GB of bf16 weig
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -54,7 +55,9 @@ class T5EncoderEngine:
             raise RuntimeError("s2v_t5_attention is specialised for d_kv = 64 (T5 v1.1 XXL and the other t5-v1_1 sizes)")
         self.L, self.H, self.eps = int(num_layers), int(num_heads), float(eps)
         self.num_buckets, self.max_distance = int(num_buckets), int(max_distance)
-        emb = state["shared.weight"]
+        # transformers ties encoder.embed_tokens to `shared`; the encoder's forward reads embed_tokens, so that name wins when a module
+        # was built with the tie broken (e.g. materialised from the meta device)
+        emb = state["encoder.embed_tokens.weight"] if "encoder.embed_tokens.weight" in state else state["shared.weight"]
         self.device = emb.device
         if self.device.type != "cuda":
             raise RuntimeError("T5EncoderEngine needs the text encoder on a CUDA (B200) device; there is no CPU path")
@@ -76,6 +79,7 @@ class T5EncoderEngine:
         self.inner = self.H * 64
         self.ones = torch.ones(1, self.D, device=self.device, dtype=torch.float32)     # gate table of the residual epilogue: h += 1 * y
         self._bias: Dict[int, torch.Tensor] = {}
+        self._graphs: Dict[tuple, object] = {}       # (B, S) -> False (seen once) | (CUDAGraph, static ids, static output)
 
     def position_bias(self, S: int) -> torch.Tensor:
         """[H, S, S] bf16: relative_attention_bias gathered by bucket (T5Attention.compute_bias; no mask term — the pipeline passes none)."""
@@ -91,12 +95,34 @@ class T5EncoderEngine:
 
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor) -> torch.Tensor:
+        """One encode.  The ~200 launches of a call are short (a 226-token prompt keeps every GEMM at the weight-streaming bound), so the
+        call is launch-bound from Python: per (batch, sequence) shape the launch sequence is captured ONCE into a CUDA graph on static
+        buffers and replayed (S2V_T5_GRAPH=0 keeps direct launches; the first call of a shape runs eagerly and is the warm-up)."""
         if input_ids.dim() != 2:
             raise ValueError("input_ids must be [batch, sequence]")
-        B, S = input_ids.shape
+        ids = input_ids.to(device=self.device, dtype=torch.long).contiguous()
+        if os.environ.get("S2V_T5_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
+            return self._forward_eager(ids)
+        key = tuple(ids.shape)
+        ent = self._graphs.get(key)
+        if ent is None:                              # first call of this shape: eager (also loads / warms every kernel)
+            self._graphs[key] = False
+            return self._forward_eager(ids)
+        if ent is False:                             # second call: capture
+            static_ids = ids.clone()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward_eager(static_ids)
+            ent = self._graphs[key] = (graph, static_ids, static_out)
+        graph, static_ids, static_out = ent
+        static_ids.copy_(ids)
+        graph.replay()
+        return static_out.clone()
+
+    def _forward_eager(self, ids: torch.Tensor) -> torch.Tensor:
+        B, S = ids.shape
         dev, D, H, M = self.device, self.D, self.H, B * S
         st = torch.cuda.current_stream().cuda_stream
-        ids = input_ids.to(device=dev, dtype=torch.long).contiguous()
         e = lambda *shape: torch.empty(*shape, device=dev, dtype=BF16)  # noqa: E731
         h, xn, qkv, att = e(M, D), e(M, D), e(M, 3 * self.inner), e(M, self.inner)
         g, act = e(M, 2 * self.F), e(M, self.F)

@@ -41,8 +41,11 @@ if not cfgs:
             "bk80_hi_mc_s400": (7, 1, 400)}
 
 
+USE_DBG = os.environ.get("DBG", "1") == "1"      # DBG=0: no per-CTA counters (thread 0's clock reads delay softmax warp 0 at the start)
+
+
 def run_exp(c, o):
-    rc = exp.s2v_attn_fwd_exp(qkv.data_ptr(), o.data_ptr(), B, S, H, 0.125, c[0], c[1], c[2], dbg.data_ptr(),
+    rc = exp.s2v_attn_fwd_exp(qkv.data_ptr(), o.data_ptr(), B, S, H, 0.125, c[0], c[1], c[2], dbg.data_ptr() if USE_DBG else None,
                               torch.cuda.current_stream().cuda_stream)
     if rc:
         raise RuntimeError(f"s2v_attn_fwd_exp rc={rc}: {exp.s2v_last_error().decode()}")
@@ -88,6 +91,15 @@ for name, c in cfgs.items():
     print(json.dumps({"variant": name, "spec": c, "max_abs_vs_shipped": float((o.float() - ref.float()).abs().max())}), flush=True)
 
 arms = {"sdpa": (run_sdpa, None), "shipped": (run_shipped, None)}
+_old_path = os.path.join(ROOT, "tools", "bin", "libs2v_old.so")      # optional: a previous build of the product library as its own arm
+if os.path.exists(_old_path) and os.environ.get("OLD", "0") == "1":
+    _old = C.CDLL(_old_path)
+    _old.s2v_attn_fwd.argtypes = [vp, vp, i32, i32, i32, C.c_float, vp]
+
+    def run_old(_c, o):
+        assert _old.s2v_attn_fwd(qkv.data_ptr(), o.data_ptr(), B, S, H, 0.125, torch.cuda.current_stream().cuda_stream) == 0
+
+    arms["old_build"] = (run_old, None)
 arms.update({k: (run_exp, c) for k, c in cfgs.items()})
 for k, (fn, c) in arms.items():   # warm the clocks
     timed(fn, c)

@@ -24,6 +24,7 @@ with torch.no_grad():
             p.copy_(1 + 0.1 * torch.randn(p.shape, device=dev, generator=g))
         else:
             p.copy_(torch.randn(p.shape, device=dev, generator=g) / p.shape[-1] ** 0.5 * (0.1 if (".q." in n or ".k." in n) else 1.0))
+    m.encoder.embed_tokens.weight = m.shared.weight        # to_empty() breaks the tie; a loaded checkpoint has it
 ids = torch.randint(0, 32128, (2, 226), device=dev, generator=g)
 
 
