@@ -20,7 +20,7 @@ vp, i32 = C.c_void_p, C.c_int32
 exp.s2v_attn_fwd_exp.argtypes = [vp, vp, i32, i32, i32, C.c_float, i32, i32, i32, vp, vp]
 OFF, NT, NS = 2 + 3 * 76 * 48 * 2, 16, 6
 dbg = torch.zeros(OFF + 8 * NT * NS + 2 * NT * 2 + 16, dtype=torch.int64, device="cuda")
-variant = int(sys.argv[1]) if len(sys.argv) > 1 else (9 << 4)
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 for _ in range(3):
     dbg.zero_()
     rc = exp.s2v_attn_fwd_exp(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, variant, 1, 200, dbg.data_ptr(), torch.cuda.current_stream().cuda_stream)
