@@ -52,6 +52,8 @@ mod = torch.randn(B, 6 * D, device=dev)
 report("adaln_modulate (read + write [B,S,D] bf16)", 2 * x.numel() * 2,
        timed(lambda: ops.adaln_modulate(x, out, w, b, mod, shift_off_text=3 * D, scale_off_text=4 * D, shift_off_other=0, scale_off_other=D,
                                         text_len=L, eps=1e-5)))
+torch.cuda.synchronize()
+print(json.dumps({"adaln_output_checksum": int(out.view(torch.int16).to(torch.int64).sum().item())}), flush=True)
 qkv = torch.randn(B, S, 3 * D, device=dev).to(BF16)
 nw = [(1 + 0.1 * torch.randn(64, device=dev)).to(BF16) for _ in range(2)]
 nb = [(0.1 * torch.randn(64, device=dev)).to(BF16) for _ in range(2)]
