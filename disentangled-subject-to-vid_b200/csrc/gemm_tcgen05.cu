@@ -20,6 +20,11 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_GROUP_M_DEFAULT = 16;
 constexpr int GEMM_THREADS = 192;
+// The fused q/k LayerNorm + RoPE epilogue is ~5x the plain one per element: with 4 epilogue warps it took longer than the tile's main
+// loop (tensor pipe 76 % in ncu, profiles/r02_qkv_fused_ncu_full.txt).  That instantiation runs 8 epilogue warps — two per TMEM
+// lane quarter, each taking half of the tile's head vectors.
+constexpr int GEMM_THREADS_WIDE_EPI = 320;
+__host__ __device__ constexpr int gemm_threads(int epi) { return epi == 4 /* S2V_EPI_QKV_NORM_ROPE */ ? GEMM_THREADS_WIDE_EPI : GEMM_THREADS; }
 
 struct GemmKParams {
     int M, N, K, K2;
@@ -131,7 +136,7 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
 }
 
 template <int BN, int EPI, bool TWO>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                     const GemmKParams p) {
@@ -176,7 +181,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], TWO ? 8 : 4);  // one arrive per epilogue warp (of both CTAs: the leader's MMA thread waits)
+            // one arrive per epilogue warp (of both CTAs: the leader's MMA thread waits)
+            mbar_init(&tmem_empty[a], (TWO ? 2 : 1) * (gemm_threads(EPI) / 32 - 2));
         }
         fence_barrier_init();
     }
@@ -298,8 +304,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..5; 2..9 for the fused q/k epilogue)
         const int q = warp & 3;  // TMEM lane quarter this warp may touch
+        const int ehalf = (warp - 2) >> 2;   // 8 epilogue warps: which half of the tile's head vectors this warp takes
+        // fused q/k epilogue: per-warp staging of the parameters every lane reads at the same address — the tile's bias slice
+        // (BN bf16) and the four 64-wide LayerNorm vectors — in the (otherwise unused) statistics area: as global loads each use sat
+        // behind a full L1/L2 round trip inside loops that are not unrolled (44 % long-scoreboard stalls in ncu)
+        uint8_t* ep_s = reinterpret_cast<uint8_t*>(stat_red) + (warp - 2) * 1024;     // [0, 512) bias slice, [512, 1024) nq_w | nq_b | nk_w | nk_b
+        if (EPI == S2V_EPI_QKV_NORM_ROPE) {
+            const bf16* src = lane < 8 ? p.nq_w : lane < 16 ? p.nq_b : lane < 24 ? p.nk_w : p.nk_b;
+            sts128(ep_s + 512 + lane * 16, __ldg(reinterpret_cast<const uint4*>(src) + (lane & 7)));
+            __syncwarp();
+        }
         int it = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             int m_blk, n_blk;
@@ -367,7 +383,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) mbar_arrive_relaxed(&tmem_empty[acc]);
                 continue;
             }
             const int row = m_blk * GEMM_BM + q * 32 + lane;
@@ -394,15 +410,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // that the row's cos / sin (uncoalesced: one table row per thread) are read ONCE per tile instead of once per head
                 // vector.  Same arithmetic as head_norm_rope / qk_norm_rope_kernel.
                 constexpr int NH = BN / 64;
+                if (lane * 8 < BN) {
+                    uint4 bz = make_uint4(0u, 0u, 0u, 0u);
+                    if (p.bias && n0 + lane * 8 < p.N) bz = __ldg(reinterpret_cast<const uint4*>(p.bias + n0) + lane);
+                    sts128(ep_s + lane * 16, bz);
+                }
+                __syncwarp();
                 const int sidx = row_ok ? row % p.rows_per_batch : 0;
                 const bool rope = p.rope_cos != nullptr && sidx >= p.text_len;
                 const float* cs = p.rope_cos + (long long)(rope ? sidx - p.text_len : 0) * 64;
                 const float* sn = p.rope_sin + (long long)(rope ? sidx - p.text_len : 0) * 64;
                 const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-                const bool qk_tile = n0 < p.qk_cols;   // at least the first head vector is a q or k head
+                const bool qk_tile = n0 + (ehalf * (BN / 128)) * 64 < p.qk_cols;   // at least this warp's first head vector is a q or k head
                 float mean[NH], rstd[NH];
+                constexpr int NHW = NH / 2;                 // head vectors per epilogue warp
+                const int hv_lo = ehalf * NHW, hv_hi = hv_lo + NHW;
 #pragma unroll 1
-                for (int hv = 0; hv < NH; ++hv) {
+                for (int hv = hv_lo; hv < hv_hi; ++hv) {
                     uint32_t v0[32], v1[32];
                     tmem_ld32(trow + hv * 64, v0);
                     tmem_ld32(trow + hv * 64 + 32, v1);
@@ -417,7 +441,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (p.bias && col0 < p.N) {
 #pragma unroll
                         for (int v8 = 0; v8 < 8; ++v8) {
-                            const uint4 bb = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + v8);
+                            const uint4 bb = lds128(ep_s + (hv * 64 + v8 * 8) * 2);
                             const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -476,20 +500,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             }
                         }
 #pragma unroll 1
-                        for (int hv = 0; hv < NH; ++hv) {
+                        for (int hv = hv_lo; hv < hv_hi; ++hv) {
                             uint32_t v[16];
                             tmem_ld16(trow + hv * 64 + c16 * 16, v);
                             tmem_ld_wait();
                             const int col0 = n0 + hv * 64 + c16 * 16;
                             if (!(row_ok && col0 < p.qk_cols)) continue;   // v head vectors were stored by pass 1
                             const bool is_q = col0 < (p.qk_cols >> 1);
-                            const bf16* nw = is_q ? p.nq_w : p.nk_w;
-                            const bf16* nb = is_q ? p.nq_b : p.nk_b;
+                            const uint8_t* nw = ep_s + (is_q ? 512 : 768);        // staged nq_w | nq_b | nk_w | nk_b
+                            const uint8_t* nb = nw + 128;
                             float wf[16], bfv[16];
 #pragma unroll
-                            for (int v8 = 0; v8 < 2; ++v8) {   // same address in every lane: one L1 wavefront each
-                                const uint4 wu = __ldg(reinterpret_cast<const uint4*>(nw) + c16 * 2 + v8);
-                                const uint4 bu = __ldg(reinterpret_cast<const uint4*>(nb) + c16 * 2 + v8);
+                            for (int v8 = 0; v8 < 2; ++v8) {   // same address in every lane: one shared-memory wavefront each
+                                const uint4 wu = lds128(nw + (c16 * 2 + v8) * 16);
+                                const uint4 bu = lds128(nb + (c16 * 2 + v8) * 16);
                                 const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
@@ -503,7 +527,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             if (p.bias) {
 #pragma unroll
                                 for (int v8 = 0; v8 < 2; ++v8) {
-                                    const uint4 bb = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + v8);
+                                    const uint4 bb = lds128(ep_s + (hv * 64 + c16 * 16 + v8 * 8) * 2);
                                     const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                                     for (int j = 0; j < 4; ++j) {
@@ -659,7 +683,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (TWO) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+                // relaxed: the accumulator has been read (tcgen05.wait::ld); the row stores need not be visible to the issuing thread
+                if (TWO) mbar_arrive_cluster_relaxed(&tmem_empty[acc], 0); else mbar_arrive_relaxed(&tmem_empty[acc]);
             }
         }
     }
@@ -770,7 +795,7 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
         const int clusters = num_tiles < sms / 2 ? num_tiles : sms / 2;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * clusters);
-        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.blockDim = dim3(gemm_threads(EPI));
         cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -786,7 +811,7 @@ static int launch_gemm(const s2v_linear_args* a, cudaStream_t stream, const Conv
     }
     const int sms1 = conv ? sm_count() : gemm_sms();
     const int grid = num_tiles < sms1 ? num_tiles : sms1;
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+    kern<<<grid, gemm_threads(EPI), Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
     return check_launch("gemm_tcgen05_kernel");
 }
 

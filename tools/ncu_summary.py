@@ -26,7 +26,8 @@ for vals in rows[2:]:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 start = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr, data = rows[start], [r for r in rows[start + 1:] if len(r) == len(rows[start])]
+stop = next((i for i in range(start + 1, len(rows)) if rows[i] and rows[i][0] == "Address"), len(rows))   # first launch only
+hdr, data = rows[start], [r for r in rows[start + 1:stop] if len(r) == len(rows[start])]
 ix = {h: i for i, h in enumerate(hdr)}
 tot = sum(int(r[ix["# Samples"]]) for r in data)
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
