@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
     if jobs or not os.path.exists(LIB_PATH):
-        run([nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"])
+        run([nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB_PATH, *objs, "-lcudart"])
     return LIB_PATH
 
 

@@ -21,7 +21,7 @@ def build():
         obj = os.path.join(ROOT, "tools", "bin", name + "_exp.o")
         subprocess.run([b._nvcc(), *b.NVCC_FLAGS, *extra, "-c", os.path.join(src_dir, name + ".cu"), "-o", obj], check=True)
         objs.append(obj)
-    subprocess.run([b._nvcc(), "-shared", "-o", OUT, *objs, "-lcudart"], check=True)
+    subprocess.run([b._nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT, *objs, "-lcudart"], check=True)
     return OUT
 
 
