@@ -107,10 +107,16 @@ __device__ __forceinline__ uint32_t clock32() {
     return c;
 }
 
-template <int BK, int POLY16, bool HI, bool MC, bool TRACE = false>
+// PAIR (template flag, experiment library only): the two CTAs of the cluster issue ONE tcgen05.mma.cta_group::2 stream (M 256 x N 64: the
+// leader's 128 query rows of a chain and the peer's) from the leader's thread.  Each CTA stages only ITS half of every K tile (32 key
+// rows) and of every V tile (all 64 keys x 32 of the 64 channels, 64-byte swizzle) — no multicast: shared-memory operand reads, stores and
+// footprint per SM halve.  P is complete when the softmax warps of BOTH CTAs have arrived on the leader's p_ready (count 8, the peer's
+// arrive remotely); score-ready, P-consumed, stage-free and final commits are multicast to both CTAs.
+template <int BK, int POLY16, bool HI, bool MC, bool TRACE = false, bool PAIR = false>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H,
-                float scale_log2, int skew_ns, unsigned long long* __restrict__ dbg) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ qkv,
+                bf16* __restrict__ out, int S, int H, float scale_log2, int skew_ns, unsigned long long* __restrict__ dbg) {
+    static_assert(!PAIR || (MC && BK == 64 && !TRACE), "PAIR: a 2-CTA cluster, 64-key tiles");
     constexpr int W_TMA = HI ? 8 : 0, W_MMA = HI ? 9 : 1, W_SOFT0 = HI ? 0 : 4;   // warp roles (see the header comment)
     constexpr int ATT_BK = BK;
     constexpr uint32_t ATT_TILE_BYTES = att_tile_bytes(BK);
@@ -142,28 +148,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
     const int n_kv = (S + ATT_BK - 1) / ATT_BK;
     // MC: grid.x is rounded up to a whole number of clusters; a CTA whose query block lies beyond S only keeps the K/V
     // exchange with its partner going (it loads and multicasts its halves and releases the ring stages)
-    const bool active = !MC || q_row0 < S;
+    const bool active = !MC || PAIR || q_row0 < S;     // PAIR: a CTA beyond S computes on zero queries (its rows are not stored)
     const uint32_t cta_rank = MC ? cluster_ctarank() : 0u;
 
     if (warp == W_TMA && lane == 0) {
         tma_prefetch_desc(&tmQKV);
         for (int s = 0; s < ATT_STAGES; ++s) {
             mbar_init(&kv_full[s], 1);
-            mbar_init(&kv_empty[s], MC ? 2 : 1);     // MC: one tcgen05.commit arrive from each CTA of the pair
+            mbar_init(&kv_empty[s], (MC && !PAIR) ? 2 : 1);     // MC: one tcgen05.commit arrive from each CTA of the pair
         }
         for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
         // p_ready is double buffered by tile parity: without a per-tile p_free wait a fast softmax warp may finish tile t+1
         // before a slow one has arrived for tile t (it cannot get further: S(t+2) is only issued after p_ready(t)), and
         // two arrivals of one warp must never land in the same barrier phase.
-        for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], 4);  // one arrive per softmax warp of the query tile
+        for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], PAIR ? 8 : 4);  // one arrive per softmax warp of the query tile (PAIR: of both CTAs)
         for (int q = 0; q < 2; ++q) mbar_init(&p_free[q], 1);
-        mbar_init(q_ready, 8);
+        mbar_init(q_ready, PAIR ? 16 : 8);
         mbar_init(o_final, 1);
         fence_barrier_init();
     }
     __syncwarp();
     if (MC) cluster_sync_all();   // the partner's barriers exist before anything is multicast into this CTA
-    if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
+    if (warp == W_MMA) {
+        if (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -178,6 +186,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 uint32_t phase = 0;
                 for (int t = 0; t < n_kv; ++t) {
                     mbar_wait(&kv_empty[stage], phase ^ 1);
+                    if (PAIR) {
+                        // the leader's barrier counts the bytes of both CTAs' halves (the peer's loads signal it: cta_group::2)
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+                        tma_load_4d_pair(&tmQKV, &kv_full[stage], sK + stage * ATT_TILE_BYTES, 0, H + head, t * ATT_BK + int(cta_rank) * (ATT_BK / 2), batch);
+                        tma_load_4d_pair(&tmV, &kv_full[stage], sV + stage * ATT_TILE_BYTES, int(cta_rank) * (ATT_D / 2), 2 * H + head, t * ATT_BK, batch);
+                        if (++stage == ATT_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
                     if (MC) {   // this CTA's half (32 key rows = 4 swizzle atoms) of K(t) and V(t), delivered to both CTAs
                         const uint32_t half = cta_rank * (ATT_TILE_BYTES / 2);
@@ -196,30 +215,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
             }
         } else if (warp == W_MMA) {
             // ---------------------------------------------------------------- MMA issuer
-            constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BK, 0, 0);   // S = Q K^T   (A in TMEM, B K-major)
-            constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_D, 0, 1);    // O += P V    (A in TMEM, B MN-major)
+            constexpr uint32_t idesc_s = make_idesc_bf16(PAIR ? 2 * ATT_BQ : ATT_BQ, ATT_BK, 0, 0);   // S = Q K^T   (A in TMEM, B K-major)
+            constexpr uint32_t idesc_o = make_idesc_bf16(PAIR ? 2 * ATT_BQ : ATT_BQ, ATT_D, 0, 1);    // O += P V    (A in TMEM, B MN-major)
             auto issue_s = [&](int q, int stage, int buf) {
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + stage * ATT_TILE_BYTES), 16, 1024);
 #pragma unroll
-                for (int k = 0; k < ATT_D / 16; ++k)
-                    umma_ts(tmem_base + TM_S + (q * 2 + buf) * BK, tmem_base + TM_Q + q * 32 + k * 8, bdesc + uint64_t(k * 2),
-                            idesc_s, k != 0);
+                for (int k = 0; k < ATT_D / 16; ++k) {
+                    if (PAIR) umma_ts_pair(tmem_base + TM_S + (q * 2 + buf) * BK, tmem_base + TM_Q + q * 32 + k * 8, bdesc + uint64_t(k * 2), idesc_s, k != 0);
+                    else umma_ts(tmem_base + TM_S + (q * 2 + buf) * BK, tmem_base + TM_Q + q * 32 + k * 8, bdesc + uint64_t(k * 2), idesc_s, k != 0);
+                }
             };
             auto issue_pv = [&](int q, int stage, bool accumulate, int t) {
                 // V tile [BK keys][64 d]: 16 keys per MMA = two 8-row groups = 2048 bytes
+                if (PAIR) {
+                    // this CTA's slab [BK keys][32 channels], 64-byte rows, 64-byte swizzle: 16 keys per MMA = two 8-row groups = 1024 bytes
+                    const uint64_t bd = make_smem_desc_sw64(smem_u32(sV + stage * ATT_TILE_BYTES), 512, 512);
+#pragma unroll
+                    for (int k = 0; k < ATT_BK / 16; ++k)
+                        umma_ts_pair(tmem_base + TM_O + q * 64, tmem_base + TM_S + (q * 2 + (t & 1)) * BK + k * 8, bd + uint64_t(k * 64), idesc_o,
+                                     (accumulate || k != 0) ? 1u : 0u);
+                    return;
+                }
                 const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + stage * ATT_TILE_BYTES), 1024, 1024);
 #pragma unroll
                 for (int k = 0; k < ATT_BK / 16; ++k)
                     umma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_S + (q * 2 + (t & 1)) * BK + k * 8, bdesc + uint64_t(k * 128), idesc_o,
                             (accumulate || k != 0) ? 1u : 0u);
             };
+            // commits: PAIR -> the barrier at this offset in BOTH CTAs
+            auto commit = [&](uint64_t* bar) {
+                if (PAIR) umma_commit_pair(bar, 3); else umma_commit(bar);
+            };
             auto release_kv = [&](int stage) {
-                if (MC) umma_commit_mcast(&kv_empty[stage], 3); else umma_commit(&kv_empty[stage]);
+                if (PAIR) umma_commit_pair(&kv_empty[stage], 3);
+                else if (MC) umma_commit_mcast(&kv_empty[stage], 3);
+                else umma_commit(&kv_empty[stage]);
             };
             // The whole issue loop runs in ONE elected thread: with `elect.sync` the compiler knows a single lane is
             // active and feeds tcgen05.mma's uniform-register operands directly; under `if (lane == 0)` it wrapped every
             // MMA in a warp-uniformisation loop (~80 issue cycles per MMA, which made the issuer the bottleneck).
-            if (elect_one()) {
+            if ((!PAIR || cta_rank == 0) && elect_one()) {     // PAIR: the leader CTA's thread issues for both
                 // ---- decoupled issue: each query tile has its own chain.  When P_q(t) is ready: PV_q(t), then
                 // S_q(t+2) straight into the buffer PV_q(t) has just consumed (in-order tensor pipe).  S_q(t+1) was issued
                 // when q finished tile t-1, so every warpgroup has a full tile of slack that does not depend on the other one.
@@ -242,9 +277,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                 for (int t = 0; t < 2 && t < n_kv; ++t) {
                     need_kv(t);
                     issue_s(0, t % ATT_STAGES, t & 1);
-                    umma_commit(&s_full[t & 1]);
+                    commit(&s_full[t & 1]);
                     issue_s(1, t % ATT_STAGES, t & 1);
-                    umma_commit(&s_full[2 + (t & 1)]);
+                    commit(&s_full[2 + (t & 1)]);
                 }
                 int tq[2] = {0, 0};
                 while (tq[0] < n_kv || tq[1] < n_kv) {
@@ -261,11 +296,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                             if (TRACE && tracing && t >= ATT_TRACE_T0 && t < ATT_TRACE_T0 + ATT_TRACE_NT)
                                 dbg[ATT_TRACE_OFF + 8 * ATT_TRACE_NT * ATT_TRACE_STAMPS + (q * ATT_TRACE_NT + (t - ATT_TRACE_T0)) * 2] = clock32();
                             issue_pv(q, t % ATT_STAGES, t != 0, t);
-                            umma_commit(&p_free[q]);
+                            commit(&p_free[q]);
                             if (t + 2 < n_kv) {
                                 need_kv(t + 2);
                                 issue_s(q, (t + 2) % ATT_STAGES, t & 1);
-                                umma_commit(&s_full[q * 2 + (t & 1)]);
+                                commit(&s_full[q * 2 + (t & 1)]);
                             }
                             if (TRACE && tracing && t >= ATT_TRACE_T0 && t < ATT_TRACE_T0 + ATT_TRACE_NT)
                                 dbg[ATT_TRACE_OFF + 8 * ATT_TRACE_NT * ATT_TRACE_STAMPS + (q * ATT_TRACE_NT + (t - ATT_TRACE_T0)) * 2 + 1] = clock32();
@@ -274,7 +309,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
                         }
                     }
                 }
-                umma_commit(o_final);
+                commit(o_final);
                 }
             }
             __syncwarp();
@@ -308,7 +343,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(q_ready);
+            if (lane == 0) {
+                if (PAIR && cta_rank != 0) mbar_arrive_cluster(q_ready, 0); else mbar_arrive(q_ready);
+            }
         }
 
         // Start the second query tile's softmax half a tile late: with both warpgroups in lock-step they fight for the
@@ -439,7 +476,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
             if (TRACE) st4 = clock32();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_ready[q * 2 + buf]);
+            if (lane == 0) {
+                // (relaxed: P is in TMEM and complete — tcgen05.wait::st above; a release at cluster scope costs a full memory fence per tile)
+                if (PAIR && cta_rank != 0) mbar_arrive_cluster_relaxed(&p_ready[q * 2 + buf], 0); else mbar_arrive(&p_ready[q * 2 + buf]);
+            }
             if (TRACE && tracing && lane == 0 && t >= ATT_TRACE_T0 && t < ATT_TRACE_T0 + ATT_TRACE_NT) {
                 unsigned long long* r = dbg + ATT_TRACE_OFF + ((warp - W_SOFT0) * ATT_TRACE_NT + (t - ATT_TRACE_T0)) * ATT_TRACE_STAMPS;
                 r[0] = st0; r[1] = st1; r[2] = st2; r[3] = st3; r[4] = st4; r[5] = clock32();
@@ -473,13 +513,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restric
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // the pair's TMEM is freed only when neither CTA's MMAs / arrivals can still touch it
     if (warp == W_MMA) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
     // MC: neither CTA may retire while the partner can still multicast into its shared memory or arrive on its barriers
     __syncwarp();
-    if (MC) cluster_sync_all();
+    if (MC && !PAIR) cluster_sync_all();
     if (dbg && threadIdx.x == 0) {   // profiling aid: per-CTA SM cycles and wall nanoseconds -> effective SM clock of this launch
         unsigned long long t1;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
@@ -514,10 +555,10 @@ constexpr int ATT_SKEW_NS_DEFAULT = 200;
 #define S2V_ATTN_BK 64
 #endif
 
-using attn_kern_t = void (*)(const CUtensorMap, const bf16*, bf16*, int, int, float, int, unsigned long long*);
+using attn_kern_t = void (*)(const CUtensorMap, const CUtensorMap, const bf16*, bf16*, int, int, float, int, unsigned long long*);
 
 int launch_attn(attn_kern_t kern, int bk, bool mc, const void* qkv, void* o, int B, int S, int H, float softmax_scale, int skew_ns,
-                unsigned long long* dbg, cudaStream_t stream, const char* who) {
+                unsigned long long* dbg, cudaStream_t stream, const char* who, bool pair = false) {
     if (!qkv || !o) return set_error(S2V_E_BADARG, "s2v_attn_fwd: null pointer");
     if (B <= 0 || S <= 0 || H <= 0) return set_error(S2V_E_BADARG, "s2v_attn_fwd: empty problem");
     if (B > 65535 || H > 65535) return set_error(S2V_E_UNSUPPORTED, "s2v_attn_fwd: B and H must fit a grid dimension");
@@ -529,6 +570,11 @@ int launch_attn(attn_kern_t kern, int bk, bool mc, const void* qkv, void* o, int
     const uint64_t strides[4] = {2, (uint64_t)ATT_D * 2, row_bytes, row_bytes * (uint64_t)S};
     const uint32_t box[4] = {ATT_D, 1, uint32_t(mc ? bk / 2 : bk), 1};
     if ((rc = make_tmap_nd_bf16(&tm, qkv, 4, dims, strides, box))) return rc;
+    CUtensorMap tmv = tm;
+    if (pair) {   // V slabs of the CTA-pair form: all keys of a tile x HALF of the channels, 64-byte rows, 64-byte swizzle
+        const uint32_t boxv[4] = {ATT_D / 2, 1, uint32_t(bk), 1};
+        if ((rc = make_tmap_nd_bf16(&tmv, qkv, 4, dims, strides, boxv, 64))) return rc;
+    }
     if ((rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), att_smem_bytes(bk), "cudaFuncSetAttribute(attn)"))) return rc;
     int qblocks = (S + ATT_BQ * ATT_QTILES - 1) / (ATT_BQ * ATT_QTILES);
     if (mc) qblocks = (qblocks + 1) & ~1;
@@ -545,7 +591,7 @@ int launch_attn(attn_kern_t kern, int bk, bool mc, const void* qkv, void* o, int
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = mc ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, static_cast<const bf16*>(qkv), static_cast<bf16*>(o), S, H, scale_log2, skew_ns, dbg);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm, tmv, static_cast<const bf16*>(qkv), static_cast<bf16*>(o), S, H, scale_log2, skew_ns, dbg);
     if (e != cudaSuccess) return set_cuda_error(e, who);
     return check_launch(who);
 }
@@ -564,6 +610,9 @@ extern "C" int s2v_attn_fwd(const void* qkv, void* o, int32_t B, int32_t S, int3
 extern "C" __attribute__((visibility("default"))) int s2v_attn_fwd_exp(const void* qkv, void* o, int32_t B, int32_t S, int32_t H,
                                                                        float softmax_scale, int32_t variant, int32_t poly16,
                                                                        int32_t skew_ns, void* dbg_u64x2, void* stream_) {
+    if (variant == 17)   // CTA-pair MMAs (cta_group::2): see PAIR above the kernel
+        return launch_attn(attn_fwd_kernel<64, 1, true, true, false, true>, 64, true, qkv, o, B, S, H, softmax_scale, skew_ns,
+                           static_cast<unsigned long long*>(dbg_u64x2), static_cast<cudaStream_t>(stream_), "attn_fwd_kernel(pair)", true);
     if (variant == 16)   // the shipped configuration with the per-phase clock trace (tools/attn_trace.py)
         return launch_attn(attn_fwd_kernel<64, 1, true, true, true>, 64, true, qkv, o, B, S, H, softmax_scale, skew_ns,
                            static_cast<unsigned long long*>(dbg_u64x2), static_cast<cudaStream_t>(stream_), "attn_fwd_kernel(trace)");

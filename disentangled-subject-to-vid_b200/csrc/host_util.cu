@@ -104,7 +104,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+                      const uint32_t* box, int swizzle_bytes) {
     EncodeTiledFn fn = get_encode();
     if (!fn) return set_error(S2V_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(S2V_E_BADARG, "TMA base must be 16-byte aligned");
@@ -122,7 +122,8 @@ int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64
         }
     }
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[128];

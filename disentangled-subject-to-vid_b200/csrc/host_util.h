@@ -21,6 +21,6 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t cols, int64_t 
                       int box_rows);
 // generic up-to-4D bf16 map: dims/strides innermost first (strides in BYTES for dims 1..rank-1)
 int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box);
+                      const uint32_t* box, int swizzle_bytes = 128);
 
 }  // namespace s2v

@@ -457,6 +457,12 @@ def test_attention_kernel_variants_match_shipped(dev, parity):
             outs[variant] = out
             assert torch.equal(out, outs[variant & 4]), (B, S, H, boost, variant)
         assert torch.equal(shipped, outs[0]) or torch.equal(shipped, outs[4])
+        # variant 17: the CTA-pair form (tcgen05.mma.cta_group::2 over the 2-CTA cluster, remote p_ready arrives, V as two 32-channel
+        # slabs with the 64-byte swizzle) — same arithmetic, same bits (incl. the O / l rescale path and a CTA whose query block lies beyond S)
+        out = torch.full((B, S, H * 64), float("nan"), device=dev, dtype=BF16)
+        assert exp.s2v_attn_fwd_exp(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, 17, 1, 200, None, torch.cuda.current_stream().cuda_stream) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(out, outs[0]), (B, S, H, boost, "pair")
         for base in (0, 4):
             parity.check(f"attention_variants[bk={80 if base else 64},B={B},S={S},H={H},boost={boost}]", rel_err(outs[base], ref)[0],
                          default=2e-2, note="torch SDPA fp32 on the same bf16 q,k,v")
