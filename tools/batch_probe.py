@@ -16,6 +16,9 @@ w = bench.WORKLOADS["cfg3"]
 dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
 model, _ = bench.build_model(w, dev)
+if os.environ.get("MERGE", "0") == "1":        # W + s B A folded once (two bf16 roundings away from the reference's unmerged arithmetic)
+    model.merge_lora = True
+    model.invalidate_engine()
 n, F, S, D = bench.geometry(w)
 pipe = s2v_b200.CustomCogVideoXPipeline(None, None, model, None, s2v_b200.CogVideoXDDIMScheduler.for_cogvideox(1.0))
 g = torch.Generator().manual_seed(0)
@@ -59,4 +62,4 @@ for rep in range(int(os.environ.get("REPS", "2"))):
     for P in (Ps if rep % 2 == 0 else Ps[::-1]):
         res[P].append(run(P, int(os.environ.get("STEPS", "3")), data[P]))
 for P in Ps:
-    print(json.dumps({"prompts_per_gpu": P, "cfg_batch": 2 * P, "runs": res[P]}), flush=True)
+    print(json.dumps({"prompts_per_gpu": P, "cfg_batch": 2 * P, "merge_lora": os.environ.get("MERGE", "0") == "1", "runs": res[P]}), flush=True)
