@@ -32,6 +32,13 @@ class LinearArgs(C.Structure):
     ]
 
 
+class SmallLinearDesc(C.Structure):
+    """include/s2v_b200.h: s2v_small_linear_desc (one problem of s2v_small_linear_batch; the array lives in DEVICE memory)."""
+    _fields_ = [("w", C.c_void_p), ("ldw", C.c_int64), ("bias", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int64),
+                ("x", C.c_void_p), ("ldx", C.c_int64), ("N", C.c_int32), ("K", C.c_int32), ("act_in", C.c_int32),
+                ("round_bf16", C.c_int32), ("alpha", C.c_float), ("beta", C.c_float)]
+
+
 class QkNormArgs(C.Structure):
     """s2v_qk_norm_args (include/s2v_b200.h)."""
 
@@ -74,6 +81,7 @@ SIGNATURES = {
     "s2v_final_norm": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_qk_norm_rope": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
     "s2v_small_linear": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _vp],
+    "s2v_small_linear_batch": [_vp, _i32, _i32, _vp, _i64, _i32, _vp],
     "s2v_timestep_sinusoid": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "s2v_patchify": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "s2v_unpatchify": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],

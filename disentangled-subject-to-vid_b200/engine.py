@@ -304,13 +304,40 @@ class TransformerEngine:
         rs = [pl.a.shape[0] for b in self.blocks for pl in (b.qkv, b.out, b.ff1, b.ff2, b.norm1, b.norm2) if pl.a is not None]
         rs += [pl.a.shape[0] for pl in (self.text_proj, self.patch_proj, self.t1, self.t2, self.no_lin, self.proj_out) if pl.a is not None]
         self.max_r = max(rs) if rs else 0
+        self._modb = None      # cached modulation batches point at the packed weights
 
     def workspace(self, B: int, S: int) -> Workspace:
         key = (B, S)
         if key not in self._ws:
             self._ws.clear()  # one geometry at a time keeps HBM use predictable
+            self._modb = None  # (its descriptors point into the old workspace)
             self._ws[key] = Workspace(B, S, self.D, self.ff_dim, self.max_r, 2 * len(self.blocks) + 1, self.device)
         return self._ws[key]
+
+    def _modulation_batches(self, ws: Workspace, B: int):
+        """The step's AdaLN modulation linears as two `s2v_small_linear_batch` problem lists (stage 1: W f(emb) + b and A f(emb) for every
+        linear; stage 2: out += s B u), built once per workspace: weight and output pointers do not change between steps."""
+        key = (id(ws), B)
+        if self._modb is not None and self._modb[0] == key:
+            return self._modb[1], self._modb[2]
+        D = self.D
+        pls = []
+        for i, pb in enumerate(self.blocks):
+            pls += [(pb.norm1, ws.mod[2 * i]), (pb.norm2, ws.mod[2 * i + 1])]
+        pls.append((self.no_lin, ws.mod[2 * len(self.blocks)][:, : 2 * D]))
+        n_lora = sum(1 for pl, _ in pls if pl.a is not None)
+        u_all = torch.empty(max(n_lora, 1), B, max(self.max_r, 8), device=self.device, dtype=torch.float32)
+        stage1, stage2 = ops.SmallLinearBatch(self.device), ops.SmallLinearBatch(self.device)
+        j = 0
+        for pl, out in pls:
+            stage1.add(pl.w, pl.b, out, None, act_in=1)
+            if pl.a is not None:
+                u = u_all[j, :, : pl.a.shape[0]]
+                j += 1
+                stage1.add(pl.a, None, u, None, act_in=1)
+                stage2.add(pl.bb, None, out, u, alpha=pl.scale, beta=1.0)
+        self._modb = (key, stage1, stage2, u_all)
+        return stage1, stage2
 
     # ------------------------------------------------------------------ forward
     def time_embed(self, timestep: torch.Tensor, B: int) -> torch.Tensor:
@@ -379,14 +406,20 @@ class TransformerEngine:
         if not self.rotary:
             ops.add_rows(ws.h, self._sincos(H // p, W // p, Fr), L + n_ref)
 
-        # ---- all modulation vectors of this step
+        # ---- all modulation vectors of this step: every block's norm1 / norm2 linear and norm_out.linear read the same time embedding, so
+        # they are ONE launch (+ one for the LoRA up-projections) instead of three per linear
         emb = self.time_embed(timestep, B)
-        scratch = torch.empty(B, max(self.max_r, 8), device=dev, dtype=torch.float32)
-        for i, pb in enumerate(self.blocks):
-            modulation(pb.norm1, emb, ws.mod[2 * i], scratch)
-            modulation(pb.norm2, emb, ws.mod[2 * i + 1], scratch)
         mod_out = ws.mod[2 * len(self.blocks)][:, : 2 * D]
-        modulation(self.no_lin, emb, mod_out, scratch)
+        if B <= 8:
+            stage1, stage2 = self._modulation_batches(ws, B)
+            stage1.run(emb, B)
+            stage2.run(None, B)
+        else:      # more than 4 prompts x 2 CFG halves: the per-linear entry point takes the rows in groups of 8
+            scratch = torch.empty(B, max(self.max_r, 8), device=dev, dtype=torch.float32)
+            for i, pb in enumerate(self.blocks):
+                modulation(pb.norm1, emb, ws.mod[2 * i], scratch)
+                modulation(pb.norm2, emb, ws.mod[2 * i + 1], scratch)
+            modulation(self.no_lin, emb, mod_out, scratch)
 
         # ---- blocks
         if self.rotary:

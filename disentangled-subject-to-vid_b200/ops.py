@@ -239,6 +239,54 @@ def small_linear(x, w, bias, out, *, act_in: int = 0, alpha: float = 1.0, beta: 
     return out
 
 
+class SmallLinearBatch:
+    """A fixed list of small-linear problems (`s2v_small_linear_batch`): descriptors are built once — weight, bias and output pointers do not
+    change between steps — and uploaded to the device; `run(x_default, B)` is ONE launch.  Problems added with x=None read x_default."""
+
+    def __init__(self, device):
+        self.device = device
+        self.items = []
+        self.keep = []          # tensors whose storage the descriptors point into
+        self.table = None
+        self.max_n = 0
+
+    def add(self, w, bias, out, x=None, *, act_in: int = 0, alpha: float = 1.0, beta: float = 0.0, round_bf16: bool = False):
+        _chk_bf16(w, "w"); _chk_f32(out, "out")
+        N, K = w.shape
+        if out.shape[-1] != N or out.stride(-1) != 1 or w.stride(1) != 1 or (K % 8) or (w.stride(0) % 8):
+            raise RuntimeError("SmallLinearBatch.add: shape / stride mismatch")
+        if x is not None:
+            _chk_f32(x, "x")
+            if x.shape[-1] != K or x.stride(-1) != 1 or (x.stride(0) % 4):
+                raise RuntimeError("SmallLinearBatch.add: x shape / stride mismatch")
+        d = _lib.SmallLinearDesc(w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(), out.stride(0), x.data_ptr() if x is not None else None,
+                                 x.stride(0) if x is not None else 0, N, K, act_in, int(round_bf16), alpha, beta)
+        self.items.append(d)
+        self.keep += [t for t in (w, bias, out, x) if t is not None]
+        self.max_n = max(self.max_n, N)
+        self.table = None
+
+    def __len__(self):
+        return len(self.items)
+
+    def run(self, x_default: Optional[torch.Tensor], B: int):
+        if not self.items:
+            return
+        if B > 8:
+            raise RuntimeError("SmallLinearBatch: B <= 8 per launch")
+        if self.table is None:
+            import ctypes as C
+            arr = (_lib.SmallLinearDesc * len(self.items))(*self.items)
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self.table = raw.to(self.device)
+        if x_default is not None:
+            _chk_f32(x_default, "x_default")
+        with _timed("s2v_small_linear_batch"):
+            _lib.check(_lib.load().s2v_small_linear_batch(self.table.data_ptr(), len(self.items), self.max_n, _ptr(x_default),
+                                                          x_default.stride(0) if x_default is not None else 0, B, _stream()),
+                       "s2v_small_linear_batch")
+
+
 def timestep_freqs(dim: int, device, freq_shift: float = 0.0) -> torch.Tensor:
     """fp32 [dim/2] frequency table, evaluated on the host with the reference's expression (embeddings.py:55-61)."""
     import math

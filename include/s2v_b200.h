@@ -132,6 +132,24 @@ S2V_API int s2v_small_linear(const float* x, int64_t ldx, const void* w, int64_t
                      int64_t ldo, int32_t B, int32_t N, int32_t K, int32_t act_in, float alpha, float beta,
                      int32_t round_bf16, void* stream);
 
+/* The same function for `count` independent problems in ONE launch (descriptors in DEVICE memory, built once per weight packing):
+ * all AdaLN modulation linears of a step (D/models/normalization.py:473-476 for every block, norm_out.linear) and, in a second
+ * launch, their LoRA up-projections — 2 launches instead of 3 per linear.  A descriptor with x == NULL reads x_default / ldx_default
+ * (the time embedding of this step).  max_n = the largest N of the batch.  Per problem the arithmetic is s2v_small_linear's. */
+typedef struct {
+    const void* w;        /* [N, K] bf16 */
+    int64_t ldw;
+    const void* bias;     /* [N] bf16 or NULL */
+    float* out;           /* [B, N] fp32 */
+    int64_t ldo;
+    const float* x;       /* [B, K] fp32, or NULL = the launch's x_default */
+    int64_t ldx;
+    int32_t N, K, act_in, round_bf16;
+    float alpha, beta;
+} s2v_small_linear_desc;
+S2V_API int s2v_small_linear_batch(const s2v_small_linear_desc* descs, int32_t count, int32_t max_n, const float* x_default,
+                                   int64_t ldx_default, int32_t B, void* stream);
+
 /* Sinusoidal timestep embedding, flip_sin_to_cos=True (D/models/embeddings.py:27-78): out[b, 0:D/2] = cos(t_b * f_i),
  * out[b, D/2:] = sin(t_b * f_i); freqs[i] = exp(-ln(10000) * i / (D/2 - freq_shift)) is tabulated by the host in fp32
  * with the reference's own expression so the argument is bit-identical; rounded through bf16 when round_bf16

@@ -790,3 +790,49 @@ def test_fp16_model_runs_in_bf16_and_returns_fp16(dev, golden_dir, parity):
     parity.check("transformer_tiny_fp16_model[plain_sincos]", rel_err(got, exact)[0], ref=rel_err(ref16, exact)[0], default=1e-2,
                  max_abs=rel_err(got, exact)[1], ref_max_abs=rel_err(ref16, exact)[1],
                  note="fp16 weights run through the bf16 engine; yardstick = the oracle executed in fp16 (the reference's 2B dtype)")
+
+
+@pytest.mark.gpu
+def test_small_linear_batch_matches_single_launches(dev):
+    """s2v_small_linear_batch (one launch for a list of problems, descriptors in device memory) computes, per problem, exactly what
+    s2v_small_linear computes: the engine's modulation path (all AdaLN linears of a step + their LoRA pairs in two launches)."""
+    from s2v_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, K = 2, 512
+    emb = torch.randn(B, K, generator=g).to(dev)
+    probs = []
+    for (N, lora) in [(18432, 128), (6144, 0), (18432, 64), (40, 8)]:
+        w = (0.05 * torch.randn(N, K, generator=g)).to(BF16).to(dev)
+        b = (0.05 * torch.randn(N, generator=g)).to(BF16).to(dev)
+        a = (0.05 * torch.randn(lora, K, generator=g)).to(BF16).to(dev) if lora else None
+        bb = (0.05 * torch.randn(N, lora, generator=g)).to(BF16).to(dev) if lora else None
+        probs.append((w, b, a, bb))
+    # reference: three single launches per problem
+    want = []
+    for (w, b, a, bb) in probs:
+        out = torch.empty(B, w.shape[0], device=dev)
+        ops.small_linear(emb, w, b, out, act_in=1)
+        if a is not None:
+            u = torch.empty(B, a.shape[0], device=dev)
+            ops.small_linear(emb, a, None, u, act_in=1)
+            ops.small_linear(u, bb, None, out, alpha=0.5, beta=1.0)
+        want.append(out)
+    s1, s2 = ops.SmallLinearBatch(dev), ops.SmallLinearBatch(dev)
+    got, us = [], []
+    for (w, b, a, bb) in probs:
+        out = torch.full((B, w.shape[0]), float("nan"), device=dev)
+        got.append(out)
+        s1.add(w, b, out, None, act_in=1)
+        if a is not None:
+            u = torch.empty(B, a.shape[0], device=dev)
+            us.append(u)
+            s1.add(a, None, u, None, act_in=1)
+            s2.add(bb, None, out, u, alpha=0.5, beta=1.0)
+    for _ in range(2):          # the second run re-uses the uploaded table (out is fully rewritten by stage 1 before stage 2 accumulates)
+        s1.run(emb, B)
+        s2.run(None, B)
+    torch.cuda.synchronize()
+    for w_, g_ in zip(want, got):
+        assert torch.equal(w_, g_)
+    from s2v_b200 import _lib
+    assert _lib.load().s2v_small_linear_batch(None, 0, 0, None, 0, 1, None) == -1
