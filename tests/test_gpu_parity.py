@@ -622,7 +622,7 @@ def test_attention_survives_a_warpgroup_that_lags_many_tiles(dev):
     base = torch.empty(B, S, H * 64, device=dev, dtype=BF16)
     ops.attention(qkv, base, H)
     outs = {}
-    for variant in range(8):   # the same source as the shipped kernel, with the start skew as a parameter
+    for variant in list(range(8)) + [17]:   # the same source as the shipped kernel, with the start skew as a parameter (17 = the CTA-pair form)
         for skew in (200, 100000):
             out = torch.empty_like(base)
             assert exp.s2v_attn_fwd_exp(qkv.data_ptr(), out.data_ptr(), B, S, H, 0.125, variant, 1, skew, None,
