@@ -61,8 +61,10 @@ int sm_count() {
 }
 
 int ensure_smem_optin(const void* kernel, int bytes, const char* what) {
-    struct Entry { const void* k; unsigned long long devs; };
-    static Entry table[64];
+    // per (kernel, device): the largest dynamic shared-memory size opted into so far (a kernel whose footprint depends on the call —
+    // the scalar T5 attention: 2 x S rows — asks again when it needs more)
+    struct Entry { const void* k; int dev; int bytes; };
+    static Entry table[256];
     static int n = 0;
     static std::mutex mu;
     int dev = 0;
@@ -70,17 +72,18 @@ int ensure_smem_optin(const void* kernel, int bytes, const char* what) {
     std::lock_guard<std::mutex> lock(mu);
     Entry* e = nullptr;
     for (int i = 0; i < n; ++i)
-        if (table[i].k == kernel) e = &table[i];
+        if (table[i].k == kernel && table[i].dev == dev) e = &table[i];
+    if (e && e->bytes >= bytes) return 0;
     if (!e) {
-        if (n == 64) return set_error(S2V_E_DRIVER, "ensure_smem_optin: kernel table full");
+        if (n == 256) return set_error(S2V_E_DRIVER, "ensure_smem_optin: kernel table full");
         e = &table[n++];
         e->k = kernel;
-        e->devs = 0;
+        e->dev = dev;
+        e->bytes = 0;
     }
-    if (e->devs & (1ull << dev)) return 0;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (err != cudaSuccess) return set_cuda_error(err, what);
-    e->devs |= 1ull << dev;
+    e->bytes = bytes;
     return 0;
 }
 

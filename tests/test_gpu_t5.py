@@ -52,8 +52,10 @@ def test_t5_kernels_vs_torch(dev, parity):
     rows = torch.empty(37, 256, device=dev, dtype=BF16)
     _lib.check(lib.s2v_gather_rows(table.data_ptr(), ids.data_ptr(), rows.data_ptr(), 37, 256, 100, st), "gather")
     assert torch.equal(rows, table[ids])
-    # attention with bias, no scaling: 226 tokens (8 keys per lane), 300 (16 per lane), 1 and 33 (ragged)
-    for (B, S, H) in [(2, 226, 3), (1, 300, 2), (1, 1, 1), (1, 33, 2)]:
+    # attention with bias, no scaling.  S <= 256 runs the tensor-core kernel (score tiles per row: 8 for S <= 64, 16 for <= 128, 30 for <= 240,
+    # 32 for <= 256 — every instantiation and its boundaries, ragged and odd sizes), longer sequences the scalar one (8 / 16 keys per lane)
+    for (B, S, H) in [(2, 226, 3), (1, 300, 2), (1, 1, 1), (1, 33, 2), (1, 64, 1), (2, 65, 1), (1, 100, 2), (1, 128, 1), (1, 129, 1), (1, 240, 1),
+                      (1, 241, 1), (1, 256, 2), (1, 257, 1), (1, 512, 1)]:
         qkv = torch.randn(B, S, 3 * H * 64, generator=g).mul(0.5).to(BF16).to(dev)
         bias = torch.randn(H, S, S, generator=g).to(BF16).to(dev)
         o = torch.full((B, S, H * 64), float("nan"), device=dev, dtype=BF16)
